@@ -1,0 +1,159 @@
+/* pg_b200.h — C ABI of libpg_b200.so, the sm_100a kernel library behind the drop-in
+ * `pytorch_generative.nn.*` / `models.*` Module API.
+ *
+ * The reference (EugenHotaj/pytorch-generative) ships no native interface: its hot path is Python
+ * nn.Modules whose arithmetic is delegated to torch.  The entry points below are
+ * therefore what a maintainer's ctypes binding would call in place of those torch ops; each one
+ * cites the reference call site it replaces.  Conventions:
+ *   - every pointer is a raw device pointer unless stated otherwise; the caller owns all memory;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - return value 0 = success, non-zero = failure with a message available from pg_last_error();
+ *   - no allocation, no global stream state, no torch/pybind types;
+ *   - activations are "pixel-major": a [P, C] row-major matrix with P = N*H*W pixels (NHWC), which is
+ *     the layout every GEMM-shaped op wants; NCHW<->pixel-major converters are provided for the
+ *     module boundary.
+ */
+#ifndef PG_B200_H_
+#define PG_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PG_ABI_VERSION 1
+
+int pg_abi_version(void);
+const char* pg_last_error(void);
+/* Number of SMs of the current device (148 on B200); used by callers to size split-K. */
+int pg_sm_count(void);
+
+/* Activation ids (shared by the GEMM epilogue and the elementwise kernels). */
+enum { PG_ACT_NONE = 0, PG_ACT_RELU = 1, PG_ACT_GELU = 2, PG_ACT_ELU = 3, PG_ACT_TANH = 4 };
+
+/* ---------------------------------------------------------------------------------------------
+ * Channel contraction (every nn.Conv2d 1x1 on the path and, per live tap, every masked conv):
+ *   reference: torch.nn.Conv2d.forward at nn/attention.py:105-118,140-144,161;
+ *   models/autoregressive/image_gpt.py:40-48,101-103; pixel_cnn.py:35-49,95-103;
+ *   gated_pixel_cnn.py:79-99,176-182; pixel_snail.py:86-87,173-180 — and their autograd
+ *   (dgrad / wgrad).
+ *
+ *   acc[m,n] = sum_k A(m,k) * B(n,k)            bf16 inputs, fp32 accumulation on tcgen05
+ *   t        = alpha * acc + bias[n]
+ *   t       *= act'(aux[m,n])                   if dact != PG_ACT_NONE   (backward through an activation)
+ *   pre      = t + res0[m,n] + res1[m,n]
+ *   out_f32[m,n]  = pre  (or += pre when accumulate=1; bias/res only added by split 0)
+ *   out_pre[m,n]  = bf16(pre)
+ *   out_bf16[m,n] = bf16(act(pre))
+ *
+ * Operand layouts: a_mn_major=0 -> A is [M,K] row-major with pitch lda (K contiguous);
+ *                  a_mn_major=1 -> A is [K,M] row-major with pitch lda (M contiguous).
+ *                  b_mn_major=0 -> B is [N,K] row-major (a conv weight [Cout,Cin]);
+ *                  b_mn_major=1 -> B is [K,N] row-major.
+ * So forward = (0,0) with B = W; dgrad = (0,1) with B = W; wgrad = (1,1) with A = dY, B = X.
+ * Pitches must be multiples of 8 elements and bases 16-byte aligned (TMA requirement).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct pg_gemm_epilogue {
+  const float* bias;   /* [N] or NULL */
+  const void* aux;     /* bf16 [M,N] pre-activation, used when dact != 0 */
+  const float* res0;   /* fp32 [M,N] or NULL */
+  const float* res1;   /* fp32 [M,N] or NULL */
+  void* out_bf16;      /* bf16 [M,N] or NULL */
+  void* out_pre;       /* bf16 [M,N] or NULL */
+  float* out_f32;      /* fp32 [M,N] or NULL */
+  int64_t ld_aux, ld_res, ld_out_bf16, ld_out_pre, ld_out_f32; /* row pitches, elements */
+  int32_t act;         /* activation applied to out_bf16 */
+  int32_t dact;        /* activation whose derivative (at aux) scales the accumulator */
+  int32_t accumulate;  /* 1: out_f32 is accumulated with fp32 atomics (split-K / grad accumulation) */
+  float alpha;
+} pg_gemm_epilogue;
+
+/* impl: 0 = tcgen05/TMA kernel (the product); 1 = plain SIMT kernel kept as an on-device cross-check
+ * for the tests (same epilogue code).  split_k >= 1 (only with accumulate=1 and no activation). */
+int pg_gemm_bf16(const void* A, int a_mn_major, int64_t lda, const void* B, int b_mn_major, int64_t ldb,
+                 int M, int N, int K, int split_k, const pg_gemm_epilogue* epi, int impl, void* stream);
+
+/* Column sums of a bf16 [P, C] matrix into fp32 out[C] (bias gradients; accumulate=1 adds). */
+int pg_colsum_bf16(const void* x, int64_t ld, int P, int C, float* out, int accumulate, void* stream);
+int pg_colsum_f32(const float* x, int64_t ld, int P, int C, float* out, int accumulate, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * NCHWLayerNorm — reference nn/convolution.py:69-75 (permute -> nn.LayerNorm(C) -> permute).
+ * Pixel-major x [P, C] fp32 (the residual stream) -> y bf16 and/or fp32; eps as nn.LayerNorm (1e-5),
+ * biased variance; mean/rstd [P] fp32 are saved for backward.
+ * Backward: dx = rstd * (g - mean_c(g) - xhat * mean_c(g * xhat)), g = dy * gamma;
+ *   dx_out_f32 = dx + dres0 + dres1 (fused residual-gradient adds), optional bf16 copy for the next
+ *   dgrad GEMM; dgamma/dbeta are accumulated (atomics) into fp32 [C] buffers that the caller zeroed.
+ * ------------------------------------------------------------------------------------------- */
+int pg_layernorm_fwd(const float* x, const float* gamma, const float* beta, int P, int C, float eps,
+                     void* y_bf16, float* y_f32, float* mean, float* rstd, void* stream);
+int pg_layernorm_bwd(const void* dy_bf16, const float* dy_f32, const float* x, const float* gamma,
+                     const float* mean, const float* rstd, int P, int C, const float* dres0,
+                     const float* dres1, float* dx_f32, void* dx_bf16, float* dgamma, float* dbeta,
+                     void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * GatedActivation — reference nn/convolution.py:46-66: act(x[:, :C]) * sigmoid(x[:, C:]).
+ * Pixel-major x [P, 2C] (bf16 or fp32) -> y [P, C].  act is PG_ACT_TANH (GatedPixelCNN) or
+ * PG_ACT_NONE (PixelSNAIL's nn.Identity).  Backward writes dx [P, 2C].
+ * ------------------------------------------------------------------------------------------- */
+int pg_gated_act_fwd(const void* x, int x_is_f32, int P, int C, int act, void* y, int y_is_f32, void* stream);
+int pg_gated_act_bwd(const void* x, int x_is_f32, const void* dy, int dy_is_f32, int P, int C, int act,
+                     void* dx, int dx_is_f32, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Recipe loss — reference models/autoregressive/image_gpt.py:158-162 (identical in the other three):
+ * BCEWithLogits(preds, x, reduction="none").sum(1).mean().  logits/target are [N, D] fp32 in any
+ * common memory order (elementwise); loss_sum receives sum over all elements (caller divides by N);
+ * dlogits = (sigmoid(l) - t) * scale.
+ * ------------------------------------------------------------------------------------------- */
+int pg_bce_logits_fwd_bwd(const float* logits, const float* target, int64_t numel, float grad_scale,
+                          float* loss_sum /* 1 float, accumulated */, float* dlogits /* or NULL */,
+                          void* stream);
+
+/* Layout converters for the Module boundary (NCHW fp32 <-> pixel-major). */
+int pg_nchw_to_pm(const float* x_nchw, int N, int C, int HW, void* out, int out_is_f32, int64_t ld_out,
+                  void* stream);
+int pg_pm_to_nchw(const void* x_pm, int x_is_f32, int64_t ld_x, int N, int C, int HW, float* out_nchw,
+                  void* stream);
+/* fp32 -> bf16 cast of a dense buffer (weights packing; masked taps already zeroed by the caller). */
+int pg_cast_f32_to_bf16(const float* x, void* y, int64_t numel, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * CausalAttention core — reference nn/attention.py:147-160 (mask, q@k^T/sqrt(dk), masked softmax,
+ * re-zero, attn@v, head concat).  q/k/v/o are pixel-major bf16 with per-image sequences of length S
+ * (seq index = row*W+col), heads are contiguous channel blocks of dk (q,k) / dv (v,o) channels.
+ * strict=1 is mask_center=True (position i attends j<i; row 0 yields zeros), strict=0 attends j<=i.
+ * scale = 1/sqrt(dk).  lse [N, H, S] fp32 (log-sum-exp of scaled scores; -inf rows store 0 with o=0).
+ * impl: 0 = tcgen05 kernel, 1 = SIMT cross-check.
+ * ------------------------------------------------------------------------------------------- */
+int pg_causal_attn_fwd(const void* q, int64_t ld_q, const void* k, int64_t ld_k, const void* v, int64_t ld_v,
+                       void* o, int64_t ld_o, float* lse, int N, int S, int H, int dk, int dv, int strict,
+                       int impl, void* stream);
+/* delta scratch: [N, H, S] fp32.  dq/dk/dv are bf16 pixel-major with the given pitches. */
+int pg_causal_attn_bwd(const void* q, int64_t ld_q, const void* k, int64_t ld_k, const void* v, int64_t ld_v,
+                       const void* o, int64_t ld_o, const void* d_o, int64_t ld_do, const float* lse,
+                       float* delta, void* dq, int64_t ld_dq, void* dk_, int64_t ld_dk, void* dv_,
+                       int64_t ld_dv, int N, int S, int H, int dk, int dv, int strict, int impl, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Tap-list convolution for small channel counts (CausalConv2d input layers, Cin in {1,3}):
+ * reference nn/convolution.py:41-43 (weight.data *= mask; F.conv2d).  x is NCHW fp32 (the model
+ * input), w is the masked OIHW fp32 weight, output pixel-major.  taps are all kh*kw positions; masked
+ * taps contribute zero because the caller zeroes the weight in place exactly as the reference does.
+ * wgrad is dense over kh*kw (masked taps receive gradient, as autograd does in the reference).
+ * ------------------------------------------------------------------------------------------- */
+int pg_conv_small_fwd(const float* x_nchw, const float* w_oihw, const float* bias, int N, int Cin, int H, int W,
+                      int Cout, int kh, int kw, int pad_h, int pad_w, float* out_f32, void* out_bf16,
+                      int act_bf16, void* stream);
+int pg_conv_small_bwd(const float* x_nchw, const float* w_oihw, const float* dy_pm /* [P,Cout] fp32 */, int N,
+                      int Cin, int H, int W, int Cout, int kh, int kw, int pad_h, int pad_w,
+                      float* dw_oihw /* accumulated */, float* dbias /* accumulated */,
+                      float* dx_nchw /* or NULL; overwritten */, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PG_B200_H_ */

@@ -1,0 +1,272 @@
+"""ctypes binding of libpg_b200.so (the C ABI declared in include/pg_b200.h).
+
+This is the only place Python touches the native library.  Tensors cross the boundary as raw device
+pointers plus sizes; the current torch CUDA stream is passed explicitly to every call, so the kernels
+are ordered with the rest of the autograd graph (forward on the main thread, backward on autograd's
+device thread).  There is deliberately NO CPU fallback: if the shared library is missing or the inputs
+are not CUDA tensors, the call raises.
+"""
+
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpg_b200.so")
+
+ACT_NONE, ACT_RELU, ACT_GELU, ACT_ELU, ACT_TANH = 0, 1, 2, 3, 4
+ACT_BY_NAME = {None: ACT_NONE, "none": ACT_NONE, "relu": ACT_RELU, "gelu": ACT_GELU, "elu": ACT_ELU, "tanh": ACT_TANH}
+
+_vp, _i32, _i64, _f32 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float
+
+
+class GemmEpilogue(ctypes.Structure):
+    """Mirror of `pg_gemm_epilogue` (include/pg_b200.h)."""
+
+    _fields_ = [
+        ("bias", _vp), ("aux", _vp), ("res0", _vp), ("res1", _vp),
+        ("out_bf16", _vp), ("out_pre", _vp), ("out_f32", _vp),
+        ("ld_aux", _i64), ("ld_res", _i64), ("ld_out_bf16", _i64), ("ld_out_pre", _i64), ("ld_out_f32", _i64),
+        ("act", ctypes.c_int32), ("dact", ctypes.c_int32), ("accumulate", ctypes.c_int32), ("alpha", _f32),
+    ]
+
+
+# name -> argtypes (restype is always int unless listed in _SPECIAL)
+_SIGNATURES = {
+    "pg_gemm_bf16": [_vp, _i32, _i64, _vp, _i32, _i64, _i32, _i32, _i32, _i32, ctypes.POINTER(GemmEpilogue), _i32, _vp],
+    "pg_colsum_bf16": [_vp, _i64, _i32, _i32, _vp, _i32, _vp],
+    "pg_colsum_f32": [_vp, _i64, _i32, _i32, _vp, _i32, _vp],
+    "pg_layernorm_fwd": [_vp, _vp, _vp, _i32, _i32, _f32, _vp, _vp, _vp, _vp, _vp],
+    "pg_layernorm_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "pg_gated_act_fwd": [_vp, _i32, _i32, _i32, _i32, _vp, _i32, _vp],
+    "pg_gated_act_bwd": [_vp, _i32, _vp, _i32, _i32, _i32, _i32, _vp, _i32, _vp],
+    "pg_bce_logits_fwd_bwd": [_vp, _vp, _i64, _f32, _vp, _vp, _vp],
+    "pg_nchw_to_pm": [_vp, _i32, _i32, _i32, _vp, _i32, _i64, _vp],
+    "pg_pm_to_nchw": [_vp, _i32, _i64, _i32, _i32, _i32, _vp, _vp],
+    "pg_cast_f32_to_bf16": [_vp, _vp, _i64, _vp],
+    "pg_causal_attn_fwd": [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
+    "pg_causal_attn_bwd": [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _vp,
+                           _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
+    "pg_conv_small_fwd": [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp],
+    "pg_conv_small_bwd": [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp],
+}
+EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + ["pg_abi_version", "pg_last_error", "pg_sm_count"])
+
+_lib = None
+
+
+def load():
+    """Loads libpg_b200.so (raises if it has not been built: there is no fallback path)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} not found: build it with `python -m pytorch_generative_b200._build` "
+            "(or __graft_entry__.build()); the CUDA path has no CPU fallback"
+        )
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.pg_last_error.restype = ctypes.c_char_p
+    lib.pg_last_error.argtypes = []
+    lib.pg_abi_version.restype = ctypes.c_int
+    lib.pg_abi_version.argtypes = []
+    lib.pg_sm_count.restype = ctypes.c_int
+    lib.pg_sm_count.argtypes = []
+    for name, argtypes in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = ctypes.c_int
+    if lib.pg_abi_version() != 1:
+        raise RuntimeError(f"libpg_b200.so ABI version {lib.pg_abi_version()} != 1")
+    _lib = lib
+    return lib
+
+
+def _check(rc, name):
+    if rc != 0:
+        raise RuntimeError(f"{name} failed: {_lib.pg_last_error().decode(errors='replace')}")
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("pytorch_generative_b200 kernels need CUDA tensors (there is no CPU fallback)")
+    return t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _pm(t):
+    """Checks a pixel-major 2-D view (unit inner stride) and returns (ptr, pitch)."""
+    assert t.dim() == 2 and t.stride(1) == 1, f"expected a [P, C] matrix with unit inner stride, got {t.shape} {t.stride()}"
+    return _ptr(t), t.stride(0)
+
+
+_sm_count = None
+
+
+def sm_count():
+    global _sm_count
+    if _sm_count is None:
+        _sm_count = load().pg_sm_count()
+    return _sm_count
+
+
+# ------------------------------------------------------------------------------------------------
+# GEMM
+# ------------------------------------------------------------------------------------------------
+def gemm(A, B, M, N, K, *, a_mn=False, b_mn=False, bias=None, aux=None, dact=ACT_NONE, res0=None, res1=None,
+         out_bf16=None, out_pre=None, out_f32=None, act=ACT_NONE, accumulate=False, alpha=1.0, split_k=1, impl=0):
+    """acc = A·Bᵀ (see pg_gemm_bf16 in include/pg_b200.h); all tensors are 2-D bf16/fp32 CUDA views."""
+    lib = load()
+    assert A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16
+    a_ptr, lda = _pm(A)
+    b_ptr, ldb = _pm(B)
+    e = GemmEpilogue()
+    e.bias = _ptr(bias)
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.numel() >= N and bias.is_contiguous()
+    ld_res = 0
+    for r in (res0, res1):
+        if r is not None:
+            assert r.dtype == torch.float32 and r.shape[0] >= M
+            p, ld = _pm(r)
+            assert ld_res in (0, ld), "res0/res1 must share a pitch"
+            ld_res = ld
+    e.res0, e.res1, e.ld_res = _ptr(res0), _ptr(res1), ld_res
+    if aux is not None:
+        assert aux.dtype == torch.bfloat16
+        e.aux, e.ld_aux = _pm(aux)
+    if out_bf16 is not None:
+        assert out_bf16.dtype == torch.bfloat16 and out_bf16.shape[0] >= M
+        e.out_bf16, e.ld_out_bf16 = _pm(out_bf16)
+    if out_pre is not None:
+        assert out_pre.dtype == torch.bfloat16 and out_pre.shape[0] >= M
+        e.out_pre, e.ld_out_pre = _pm(out_pre)
+    if out_f32 is not None:
+        assert out_f32.dtype == torch.float32 and out_f32.shape[0] >= M
+        e.out_f32, e.ld_out_f32 = _pm(out_f32)
+    e.act, e.dact, e.accumulate, e.alpha = act, dact, int(accumulate), alpha
+    _check(lib.pg_gemm_bf16(a_ptr, int(a_mn), lda, b_ptr, int(b_mn), ldb, M, N, K, split_k, ctypes.byref(e), impl,
+                            _stream()), "pg_gemm_bf16")
+
+
+def colsum(x, out, accumulate=False):
+    lib = load()
+    p, ld = _pm(x)
+    P, C = x.shape
+    assert out.dtype == torch.float32 and out.numel() >= C
+    fn = lib.pg_colsum_bf16 if x.dtype == torch.bfloat16 else lib.pg_colsum_f32
+    _check(fn(p, ld, P, C, _ptr(out), int(accumulate), _stream()), "pg_colsum")
+
+
+# ------------------------------------------------------------------------------------------------
+# LayerNorm / gated activation / loss / converters
+# ------------------------------------------------------------------------------------------------
+def layernorm_fwd(x, gamma, beta, eps, y_bf16=None, y_f32=None, mean=None, rstd=None):
+    lib = load()
+    P, C = x.shape
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    _check(lib.pg_layernorm_fwd(_ptr(x), _ptr(gamma), _ptr(beta), P, C, eps, _ptr(y_bf16), _ptr(y_f32), _ptr(mean),
+                                _ptr(rstd), _stream()), "pg_layernorm_fwd")
+
+
+def layernorm_bwd(dy, x, gamma, mean, rstd, dres0=None, dres1=None, dx_f32=None, dx_bf16=None, dgamma=None,
+                  dbeta=None):
+    lib = load()
+    P, C = x.shape
+    assert dy.is_contiguous() and x.is_contiguous()
+    dy_b = _ptr(dy) if dy.dtype == torch.bfloat16 else None
+    dy_f = _ptr(dy) if dy.dtype == torch.float32 else None
+    _check(lib.pg_layernorm_bwd(dy_b, dy_f, _ptr(x), _ptr(gamma), _ptr(mean), _ptr(rstd), P, C, _ptr(dres0),
+                                _ptr(dres1), _ptr(dx_f32), _ptr(dx_bf16), _ptr(dgamma), _ptr(dbeta), _stream()),
+           "pg_layernorm_bwd")
+
+
+def gated_act_fwd(x, y, act):
+    lib = load()
+    P, C2 = x.shape
+    assert x.is_contiguous() and y.is_contiguous() and y.shape == (P, C2 // 2)
+    _check(lib.pg_gated_act_fwd(_ptr(x), int(x.dtype == torch.float32), P, C2 // 2, act, _ptr(y),
+                                int(y.dtype == torch.float32), _stream()), "pg_gated_act_fwd")
+
+
+def gated_act_bwd(x, dy, dx, act):
+    lib = load()
+    P, C2 = x.shape
+    assert x.is_contiguous() and dy.is_contiguous() and dx.is_contiguous()
+    _check(lib.pg_gated_act_bwd(_ptr(x), int(x.dtype == torch.float32), _ptr(dy), int(dy.dtype == torch.float32), P,
+                                C2 // 2, act, _ptr(dx), int(dx.dtype == torch.float32), _stream()), "pg_gated_act_bwd")
+
+
+def bce_logits(logits, target, grad_scale, loss_sum, dlogits=None):
+    lib = load()
+    assert logits.dtype == torch.float32 and target.dtype == torch.float32
+    assert logits.is_contiguous() and target.is_contiguous() and logits.numel() == target.numel()
+    _check(lib.pg_bce_logits_fwd_bwd(_ptr(logits), _ptr(target), logits.numel(), grad_scale, _ptr(loss_sum),
+                                     _ptr(dlogits), _stream()), "pg_bce_logits_fwd_bwd")
+
+
+def nchw_to_pm(x, out):
+    """x: [N, C, H, W] fp32 contiguous -> out: [N*H*W, >=C] bf16/fp32 (pixel-major)."""
+    lib = load()
+    N, C, H, W = x.shape
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    p, ld = _pm(out)
+    _check(lib.pg_nchw_to_pm(_ptr(x), N, C, H * W, p, int(out.dtype == torch.float32), ld, _stream()), "pg_nchw_to_pm")
+
+
+def pm_to_nchw(x_pm, out):
+    lib = load()
+    N, C, H, W = out.shape
+    assert out.dtype == torch.float32 and out.is_contiguous()
+    p, ld = _pm(x_pm)
+    _check(lib.pg_pm_to_nchw(p, int(x_pm.dtype == torch.float32), ld, N, C, H * W, _ptr(out), _stream()),
+           "pg_pm_to_nchw")
+
+
+def cast_bf16(x, y):
+    lib = load()
+    assert x.dtype == torch.float32 and y.dtype == torch.bfloat16 and x.is_contiguous() and y.is_contiguous()
+    _check(lib.pg_cast_f32_to_bf16(_ptr(x), _ptr(y), x.numel(), _stream()), "pg_cast_f32_to_bf16")
+
+
+# ------------------------------------------------------------------------------------------------
+# Attention / small conv
+# ------------------------------------------------------------------------------------------------
+def causal_attn_fwd(q, k, v, o, lse, N, S, H, dk, dv, strict, impl=0):
+    lib = load()
+    (qp, ldq), (kp, ldk), (vp, ldv), (op, ldo) = _pm(q), _pm(k), _pm(v), _pm(o)
+    _check(lib.pg_causal_attn_fwd(qp, ldq, kp, ldk, vp, ldv, op, ldo, _ptr(lse), N, S, H, dk, dv, int(strict), impl,
+                                  _stream()), "pg_causal_attn_fwd")
+
+
+def causal_attn_bwd(q, k, v, o, do, lse, delta, dq, dk_, dv_, N, S, H, dk, dv, strict, impl=0):
+    lib = load()
+    (qp, ldq), (kp, ldk), (vp, ldv), (op, ldo), (dop, lddo) = _pm(q), _pm(k), _pm(v), _pm(o), _pm(do)
+    (dqp, lddq), (dkp, lddk), (dvp, lddv) = _pm(dq), _pm(dk_), _pm(dv_)
+    _check(lib.pg_causal_attn_bwd(qp, ldq, kp, ldk, vp, ldv, op, ldo, dop, lddo, _ptr(lse), _ptr(delta), dqp, lddq,
+                                  dkp, lddk, dvp, lddv, N, S, H, dk, dv, int(strict), impl, _stream()),
+           "pg_causal_attn_bwd")
+
+
+def conv_small_fwd(x, w, bias, pad, out_f32=None, out_bf16=None, act_bf16=ACT_NONE):
+    lib = load()
+    N, Cin, H, W = x.shape
+    Cout, _, kh, kw = w.shape
+    assert x.is_contiguous() and w.is_contiguous() and x.dtype == torch.float32 and w.dtype == torch.float32
+    _check(lib.pg_conv_small_fwd(_ptr(x), _ptr(w), _ptr(bias), N, Cin, H, W, Cout, kh, kw, pad[0], pad[1],
+                                 _ptr(out_f32), _ptr(out_bf16), act_bf16, _stream()), "pg_conv_small_fwd")
+
+
+def conv_small_bwd(x, w, dy_pm, pad, dw=None, dbias=None, dx=None):
+    lib = load()
+    N, Cin, H, W = x.shape
+    Cout, _, kh, kw = w.shape
+    assert dy_pm.dtype == torch.float32 and dy_pm.is_contiguous()
+    _check(lib.pg_conv_small_bwd(_ptr(x), _ptr(w), _ptr(dy_pm), N, Cin, H, W, Cout, kh, kw, pad[0], pad[1], _ptr(dw),
+                                 _ptr(dbias), _ptr(dx), _stream()), "pg_conv_small_bwd")

@@ -1,0 +1,227 @@
+// pg_attention.cu — causal attention core (reference nn/attention.py:147-160).
+//
+// Layout: q/k/v/o are pixel-major bf16 matrices; image n occupies rows [n*S, (n+1)*S); head h of q/k uses
+// columns [h*dk, (h+1)*dk), of v/o columns [h*dv, (h+1)*dv).  Position i may attend to j <= i
+// (strict=0, mask_center=False) or j < i (strict=1, mask_center=True; row 0 then has no keys and its
+// output is defined as 0, exactly what the reference's NaN -> masked_fill(0) produces).
+//
+// impl 1 (this section): SIMT kernels, one warp per row — the on-device cross-check used by the tests.
+// impl 0: tensor-core kernels (pg_attention_tc.cuh), the product path.
+#include "../../include/pg_b200.h"
+#include "pg_common.cuh"
+
+namespace {
+
+constexpr int MAX_S = 1024;   // per-warp score buffer (floats) in shared memory
+constexpr int MAX_D = 128;
+
+struct AttnArgs {
+  const bf16 *q, *k, *v, *o, *d_o;
+  bf16 *out, *dq, *dk_out, *dv_out;
+  int64_t ld_q, ld_k, ld_v, ld_o, ld_do, ld_dq, ld_dk, ld_dv;
+  float* lse;
+  const float* lse_in;
+  float* delta;
+  int N, S, H, dk, dv, strict;
+  float scale;
+};
+
+// One warp per (image, head, query row).
+__global__ void __launch_bounds__(128) attn_fwd_simt(const AttnArgs a) {
+  extern __shared__ float sm[];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  float* sc = sm + w * (MAX_S + MAX_D);   // scores
+  float* qs = sc + MAX_S;                 // the query row
+  const long long gw = (long long)blockIdx.x * 4 + w;
+  const long long total = (long long)a.N * a.H * a.S;
+  if (gw >= total) return;
+  const int i = (int)(gw % a.S);
+  const int h = (int)((gw / a.S) % a.H);
+  const int n = (int)(gw / ((long long)a.S * a.H));
+  const size_t row0 = (size_t)n * a.S;
+  for (int d = lane; d < a.dk; d += 32) qs[d] = __bfloat162float(a.q[(row0 + i) * a.ld_q + h * a.dk + d]);
+  __syncwarp();
+  const int nkeys = a.strict ? i : i + 1;
+  float m = -INFINITY;
+  for (int j = lane; j < nkeys; j += 32) {
+    const bf16* kr = a.k + (row0 + j) * a.ld_k + h * a.dk;
+    float s = 0.f;
+    for (int d = 0; d < a.dk; ++d) s = fmaf(qs[d], __bfloat162float(kr[d]), s);
+    s *= a.scale;
+    sc[j] = s;
+    m = fmaxf(m, s);
+  }
+  m = warp_max(m);
+  float l = 0.f;
+  for (int j = lane; j < nkeys; j += 32) {
+    const float p = __expf(sc[j] - m);
+    sc[j] = p;
+    l += p;
+  }
+  l = warp_sum(l);
+  __syncwarp();
+  const float inv = nkeys > 0 ? 1.f / l : 0.f;
+  for (int d = lane; d < a.dv; d += 32) {
+    float acc = 0.f;
+    for (int j = 0; j < nkeys; ++j) acc = fmaf(sc[j], __bfloat162float(a.v[(row0 + j) * a.ld_v + h * a.dv + d]), acc);
+    a.out[(row0 + i) * a.ld_o + h * a.dv + d] = __float2bfloat16(acc * inv);
+  }
+  if (lane == 0 && a.lse) a.lse[((size_t)n * a.H + h) * a.S + i] = nkeys > 0 ? m + __logf(l) : 0.f;
+}
+
+// delta[n,h,i] = sum_d dO[i,d] * O[i,d]
+__global__ void attn_delta_kernel(const AttnArgs a) {
+  const int lane = threadIdx.x & 31;
+  const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long total = (long long)a.N * a.H * a.S;
+  if (gw >= total) return;
+  const int i = (int)(gw % a.S);
+  const int h = (int)((gw / a.S) % a.H);
+  const int n = (int)(gw / ((long long)a.S * a.H));
+  const size_t row = (size_t)n * a.S + i;
+  float s = 0.f;
+  for (int d = lane; d < a.dv; d += 32)
+    s += __bfloat162float(a.d_o[row * a.ld_do + h * a.dv + d]) * __bfloat162float(a.o[row * a.ld_o + h * a.dv + d]);
+  s = warp_sum(s);
+  if (lane == 0) a.delta[((size_t)n * a.H + h) * a.S + i] = s;
+}
+
+// dQ: one warp per query row.
+__global__ void __launch_bounds__(128) attn_bwd_dq_simt(const AttnArgs a) {
+  extern __shared__ float sm[];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  float* ds = sm + w * (MAX_S + 2 * MAX_D);
+  float* qs = ds + MAX_S;
+  float* dos = qs + MAX_D;
+  const long long gw = (long long)blockIdx.x * 4 + w;
+  const long long total = (long long)a.N * a.H * a.S;
+  if (gw >= total) return;
+  const int i = (int)(gw % a.S);
+  const int h = (int)((gw / a.S) % a.H);
+  const int n = (int)(gw / ((long long)a.S * a.H));
+  const size_t row0 = (size_t)n * a.S;
+  for (int d = lane; d < a.dk; d += 32) qs[d] = __bfloat162float(a.q[(row0 + i) * a.ld_q + h * a.dk + d]);
+  for (int d = lane; d < a.dv; d += 32) dos[d] = __bfloat162float(a.d_o[(row0 + i) * a.ld_do + h * a.dv + d]);
+  __syncwarp();
+  const int nkeys = a.strict ? i : i + 1;
+  const float lse = a.lse_in[((size_t)n * a.H + h) * a.S + i];
+  const float delta = a.delta[((size_t)n * a.H + h) * a.S + i];
+  for (int j = lane; j < nkeys; j += 32) {
+    const bf16* kr = a.k + (row0 + j) * a.ld_k + h * a.dk;
+    const bf16* vr = a.v + (row0 + j) * a.ld_v + h * a.dv;
+    float s = 0.f, dp = 0.f;
+    for (int d = 0; d < a.dk; ++d) s = fmaf(qs[d], __bfloat162float(kr[d]), s);
+    for (int d = 0; d < a.dv; ++d) dp = fmaf(dos[d], __bfloat162float(vr[d]), dp);
+    const float p = __expf(s * a.scale - lse);
+    ds[j] = p * (dp - delta);
+  }
+  __syncwarp();
+  for (int d = lane; d < a.dk; d += 32) {
+    float acc = 0.f;
+    for (int j = 0; j < nkeys; ++j) acc = fmaf(ds[j], __bfloat162float(a.k[(row0 + j) * a.ld_k + h * a.dk + d]), acc);
+    a.dq[(row0 + i) * a.ld_dq + h * a.dk + d] = __float2bfloat16(acc * a.scale);
+  }
+}
+
+// dK, dV: one warp per key row j; queries i >= j (i > j when strict).
+__global__ void __launch_bounds__(128) attn_bwd_dkv_simt(const AttnArgs a) {
+  extern __shared__ float sm[];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  float* ps = sm + w * (2 * MAX_S + 2 * MAX_D);
+  float* ds = ps + MAX_S;
+  float* ks = ds + MAX_S;
+  float* vs = ks + MAX_D;
+  const long long gw = (long long)blockIdx.x * 4 + w;
+  const long long total = (long long)a.N * a.H * a.S;
+  if (gw >= total) return;
+  const int j = (int)(gw % a.S);
+  const int h = (int)((gw / a.S) % a.H);
+  const int n = (int)(gw / ((long long)a.S * a.H));
+  const size_t row0 = (size_t)n * a.S;
+  for (int d = lane; d < a.dk; d += 32) ks[d] = __bfloat162float(a.k[(row0 + j) * a.ld_k + h * a.dk + d]);
+  for (int d = lane; d < a.dv; d += 32) vs[d] = __bfloat162float(a.v[(row0 + j) * a.ld_v + h * a.dv + d]);
+  __syncwarp();
+  const int i0 = a.strict ? j + 1 : j;
+  for (int i = i0 + lane; i < a.S; i += 32) {
+    const bf16* qr = a.q + (row0 + i) * a.ld_q + h * a.dk;
+    const bf16* dor = a.d_o + (row0 + i) * a.ld_do + h * a.dv;
+    float s = 0.f, dp = 0.f;
+    for (int d = 0; d < a.dk; ++d) s = fmaf(ks[d], __bfloat162float(qr[d]), s);
+    for (int d = 0; d < a.dv; ++d) dp = fmaf(vs[d], __bfloat162float(dor[d]), dp);
+    const size_t st = ((size_t)n * a.H + h) * a.S + i;
+    const float p = __expf(s * a.scale - a.lse_in[st]);
+    ps[i - i0] = p;
+    ds[i - i0] = p * (dp - a.delta[st]);
+  }
+  __syncwarp();
+  const int cnt = a.S - i0;
+  for (int d = lane; d < a.dv; d += 32) {
+    float acc = 0.f;
+    for (int t = 0; t < cnt; ++t)
+      acc = fmaf(ps[t], __bfloat162float(a.d_o[(row0 + i0 + t) * a.ld_do + h * a.dv + d]), acc);
+    a.dv_out[(row0 + j) * a.ld_dv + h * a.dv + d] = __float2bfloat16(acc);
+  }
+  for (int d = lane; d < a.dk; d += 32) {
+    float acc = 0.f;
+    for (int t = 0; t < cnt; ++t)
+      acc = fmaf(ds[t], __bfloat162float(a.q[(row0 + i0 + t) * a.ld_q + h * a.dk + d]), acc);
+    a.dk_out[(row0 + j) * a.ld_dk + h * a.dk + d] = __float2bfloat16(acc * a.scale);
+  }
+}
+
+}  // namespace
+
+#include "pg_attention_tc.cuh"
+
+extern "C" int pg_causal_attn_fwd(const void* q, int64_t ld_q, const void* k, int64_t ld_k, const void* v,
+                                  int64_t ld_v, void* o, int64_t ld_o, float* lse, int N, int S, int H, int dk,
+                                  int dv, int strict, int impl, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  PG_REQUIRE(q && k && v && o && lse, "pg_causal_attn_fwd: null argument");
+  PG_REQUIRE(N > 0 && S > 0 && H > 0 && dk > 0 && dv > 0, "pg_causal_attn_fwd: empty problem");
+  AttnArgs a = {};
+  a.q = (const bf16*)q; a.k = (const bf16*)k; a.v = (const bf16*)v; a.out = (bf16*)o;
+  a.ld_q = ld_q; a.ld_k = ld_k; a.ld_v = ld_v; a.ld_o = ld_o;
+  a.lse = lse;
+  a.N = N; a.S = S; a.H = H; a.dk = dk; a.dv = dv; a.strict = strict;
+  a.scale = 1.0f / sqrtf((float)dk);
+  if (impl == 1) {
+    PG_REQUIRE(S <= MAX_S && dk <= MAX_D && dv <= MAX_D, "pg_causal_attn_fwd(simt): S<=%d, d<=%d", MAX_S, MAX_D);
+    const long long total = (long long)N * H * S;
+    const size_t smem = 4 * (MAX_S + MAX_D) * sizeof(float);
+    attn_fwd_simt<<<(unsigned)((total + 3) / 4), 128, smem, stream>>>(a);
+    return pg_check_launch("pg_causal_attn_fwd(simt)");
+  }
+  return attn_fwd_tc(a, stream);
+}
+
+extern "C" int pg_causal_attn_bwd(const void* q, int64_t ld_q, const void* k, int64_t ld_k, const void* v,
+                                  int64_t ld_v, const void* o, int64_t ld_o, const void* d_o, int64_t ld_do,
+                                  const float* lse, float* delta, void* dq, int64_t ld_dq, void* dk_, int64_t ld_dk,
+                                  void* dv_, int64_t ld_dv, int N, int S, int H, int dk, int dv, int strict, int impl,
+                                  void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  PG_REQUIRE(q && k && v && o && d_o && lse && delta && dq && dk_ && dv_, "pg_causal_attn_bwd: null argument");
+  PG_REQUIRE(N > 0 && S > 0 && H > 0 && dk > 0 && dv > 0, "pg_causal_attn_bwd: empty problem");
+  AttnArgs a = {};
+  a.q = (const bf16*)q; a.k = (const bf16*)k; a.v = (const bf16*)v; a.o = (const bf16*)o; a.d_o = (const bf16*)d_o;
+  a.dq = (bf16*)dq; a.dk_out = (bf16*)dk_; a.dv_out = (bf16*)dv_;
+  a.ld_q = ld_q; a.ld_k = ld_k; a.ld_v = ld_v; a.ld_o = ld_o; a.ld_do = ld_do;
+  a.ld_dq = ld_dq; a.ld_dk = ld_dk; a.ld_dv = ld_dv;
+  a.lse_in = lse; a.delta = delta;
+  a.N = N; a.S = S; a.H = H; a.dk = dk; a.dv = dv; a.strict = strict;
+  a.scale = 1.0f / sqrtf((float)dk);
+  const long long total = (long long)N * H * S;
+  attn_delta_kernel<<<(unsigned)((total * 32 + 255) / 256), 256, 0, stream>>>(a);
+  if (pg_check_launch("pg_causal_attn_bwd(delta)")) return 1;
+  if (impl == 1) {
+    PG_REQUIRE(S <= MAX_S && dk <= MAX_D && dv <= MAX_D, "pg_causal_attn_bwd(simt): S<=%d, d<=%d", MAX_S, MAX_D);
+    const size_t smem_q = 4 * (MAX_S + 2 * MAX_D) * sizeof(float);
+    const size_t smem_kv = 4 * (2 * MAX_S + 2 * MAX_D) * sizeof(float);
+    attn_bwd_dq_simt<<<(unsigned)((total + 3) / 4), 128, smem_q, stream>>>(a);
+    if (pg_check_launch("pg_causal_attn_bwd(dq simt)")) return 1;
+    attn_bwd_dkv_simt<<<(unsigned)((total + 3) / 4), 128, smem_kv, stream>>>(a);
+    return pg_check_launch("pg_causal_attn_bwd(dkv simt)");
+  }
+  return attn_bwd_tc(a, stream);
+}

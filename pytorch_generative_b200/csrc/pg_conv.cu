@@ -1,0 +1,197 @@
+// pg_conv.cu — CausalConv2d input layers with tiny Cin (1 or 3 image channels):
+// reference nn/convolution.py:41-43 called from pixel_cnn.py:86-92, pixel_snail.py:155-161,
+// image_gpt.py:87-93.  K = Cin*kh*kw is 9..49, far below a tensor-core K slab, and the layer is
+// <= 0.01 % of the step's FLOPs at the ImageGPT/PixelSNAIL configs, so this is a direct CUDA-core kernel
+// that reads the NCHW fp32 image and writes the pixel-major activation the GEMM path consumes.
+// Masked taps are zero in `w` (the caller zeroes the Parameter in place, as the reference does), so the
+// forward simply runs all kh*kw taps; wgrad is dense over the taps, matching autograd in the reference.
+#include "../../include/pg_b200.h"
+#include "pg_common.cuh"
+
+namespace {
+
+constexpr int PIX_PER_BLOCK = 32;
+constexpr int MAX_K = 160;  // Cin*kh*kw upper bound (3*7*7 = 147)
+
+struct ConvArgs {
+  int N, Cin, H, W, Cout, kh, kw, ph, pw, K;
+};
+
+// Gathers the K-vector of input values under the kernel window of pixel p (zero padding).
+__device__ __forceinline__ float patch_value(const float* __restrict__ x, const ConvArgs& a, int n, int y, int xx, int k) {
+  const int ci = k / (a.kh * a.kw);
+  const int r = k % (a.kh * a.kw);
+  const int i = r / a.kw, j = r % a.kw;
+  const int yy = y + i - a.ph, xc = xx + j - a.pw;
+  if (yy < 0 || yy >= a.H || xc < 0 || xc >= a.W) return 0.f;
+  return x[(((size_t)n * a.Cin + ci) * a.H + yy) * a.W + xc];
+}
+
+__global__ void __launch_bounds__(256)
+conv_small_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                      const ConvArgs a, float* __restrict__ out_f32, bf16* __restrict__ out_bf16, int act_bf16) {
+  __shared__ float patch[PIX_PER_BLOCK][MAX_K + 1];
+  const int HW = a.H * a.W;
+  const long long P = (long long)a.N * HW;
+  const long long p0 = (long long)blockIdx.x * PIX_PER_BLOCK;
+  for (int t = threadIdx.x; t < PIX_PER_BLOCK * a.K; t += blockDim.x) {
+    const int pi = t / a.K, k = t % a.K;
+    const long long p = p0 + pi;
+    float v = 0.f;
+    if (p < P) {
+      const int n = (int)(p / HW), rem = (int)(p % HW);
+      v = patch_value(x, a, n, rem / a.W, rem % a.W, k);
+    }
+    patch[pi][k] = v;
+  }
+  __syncthreads();
+  for (int co = threadIdx.x; co < a.Cout; co += blockDim.x) {
+    float acc[PIX_PER_BLOCK];
+    const float b = bias ? bias[co] : 0.f;
+#pragma unroll
+    for (int pi = 0; pi < PIX_PER_BLOCK; ++pi) acc[pi] = b;
+    const float* wr = w + (size_t)co * a.K;
+    for (int k = 0; k < a.K; ++k) {
+      const float wv = __ldg(wr + k);
+#pragma unroll
+      for (int pi = 0; pi < PIX_PER_BLOCK; ++pi) acc[pi] = fmaf(wv, patch[pi][k], acc[pi]);
+    }
+#pragma unroll
+    for (int pi = 0; pi < PIX_PER_BLOCK; ++pi) {
+      const long long p = p0 + pi;
+      if (p < P) {
+        if (out_f32) out_f32[p * a.Cout + co] = acc[pi];
+        if (out_bf16) out_bf16[p * a.Cout + co] = __float2bfloat16(pg_act_fwd(act_bf16, acc[pi]));
+      }
+    }
+  }
+}
+
+// wgrad: dw[co, k] += sum_p dy[p, co] * patch[p, k].  Persistent blocks; each thread owns a strided set of
+// (co, k) outputs and accumulates over the block's pixel chunks, then one atomic per output.
+constexpr int WG_PIX = 32;
+constexpr int WG_MAX_OUT_PER_THREAD = 64;
+
+__global__ void __launch_bounds__(256)
+conv_small_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, const ConvArgs a,
+                        float* __restrict__ dw) {
+  extern __shared__ float smw[];
+  float* patch = smw;                          // [WG_PIX][K]
+  float* dys = smw + WG_PIX * a.K;             // [WG_PIX][Cout]
+  const int HW = a.H * a.W;
+  const long long P = (long long)a.N * HW;
+  const int n_out = a.Cout * a.K;
+  float acc[WG_MAX_OUT_PER_THREAD];
+#pragma unroll
+  for (int i = 0; i < WG_MAX_OUT_PER_THREAD; ++i) acc[i] = 0.f;
+  for (long long p0 = (long long)blockIdx.x * WG_PIX; p0 < P; p0 += (long long)gridDim.x * WG_PIX) {
+    __syncthreads();
+    for (int t = threadIdx.x; t < WG_PIX * a.K; t += blockDim.x) {
+      const int pi = t / a.K, k = t % a.K;
+      const long long p = p0 + pi;
+      float v = 0.f;
+      if (p < P) {
+        const int n = (int)(p / HW), rem = (int)(p % HW);
+        v = patch_value(x, a, n, rem / a.W, rem % a.W, k);
+      }
+      patch[pi * a.K + k] = v;
+    }
+    for (int t = threadIdx.x; t < WG_PIX * a.Cout; t += blockDim.x) {
+      const int pi = t / a.Cout, co = t % a.Cout;
+      const long long p = p0 + pi;
+      dys[pi * a.Cout + co] = p < P ? dy[p * a.Cout + co] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < WG_MAX_OUT_PER_THREAD; ++i) {
+      const int o = threadIdx.x + i * blockDim.x;
+      if (o < n_out) {
+        const int co = o / a.K, k = o % a.K;
+        float s = 0.f;
+#pragma unroll 8
+        for (int pi = 0; pi < WG_PIX; ++pi) s = fmaf(dys[pi * a.Cout + co], patch[pi * a.K + k], s);
+        acc[i] += s;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < WG_MAX_OUT_PER_THREAD; ++i) {
+    const int o = threadIdx.x + i * blockDim.x;
+    if (o < n_out) atomicAdd(dw + o, acc[i]);
+  }
+}
+
+// dgrad w.r.t. the input image: dx[n,ci,y,x] = sum_{co,i,j} dy[(y-i+ph, x-j+pw), co] * w[co,ci,i,j].
+// One warp per input pixel, lanes over output channels.
+__global__ void __launch_bounds__(256)
+conv_small_dgrad_kernel(const float* __restrict__ w, const float* __restrict__ dy, const ConvArgs a,
+                        float* __restrict__ dx) {
+  const int lane = threadIdx.x & 31;
+  const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int HW = a.H * a.W;
+  const long long P = (long long)a.N * HW;
+  if (gw >= P) return;
+  const int n = (int)(gw / HW), rem = (int)(gw % HW);
+  const int y = rem / a.W, xx = rem % a.W;
+  for (int ci = 0; ci < a.Cin; ++ci) {
+    float acc = 0.f;
+    for (int i = 0; i < a.kh; ++i) {
+      const int yo = y - i + a.ph;
+      if (yo < 0 || yo >= a.H) continue;
+      for (int j = 0; j < a.kw; ++j) {
+        const int xo = xx - j + a.pw;
+        if (xo < 0 || xo >= a.W) continue;
+        const float* dyr = dy + ((size_t)n * HW + (size_t)yo * a.W + xo) * a.Cout;
+        for (int co = lane; co < a.Cout; co += 32)
+          acc = fmaf(dyr[co], __ldg(w + (((size_t)co * a.Cin + ci) * a.kh + i) * a.kw + j), acc);
+      }
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) dx[(((size_t)n * a.Cin + ci) * a.H + y) * a.W + xx] = acc;
+  }
+}
+
+}  // namespace
+
+extern "C" int pg_conv_small_fwd(const float* x_nchw, const float* w_oihw, const float* bias, int N, int Cin, int H,
+                                 int W, int Cout, int kh, int kw, int pad_h, int pad_w, float* out_f32,
+                                 void* out_bf16, int act_bf16, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  PG_REQUIRE(x_nchw && w_oihw && (out_f32 || out_bf16), "pg_conv_small_fwd: null argument");
+  ConvArgs a = {N, Cin, H, W, Cout, kh, kw, pad_h, pad_w, Cin * kh * kw};
+  PG_REQUIRE(a.K <= MAX_K, "pg_conv_small_fwd: Cin*kh*kw = %d exceeds %d", a.K, MAX_K);
+  const long long P = (long long)N * H * W;
+  const unsigned blocks = (unsigned)((P + PIX_PER_BLOCK - 1) / PIX_PER_BLOCK);
+  conv_small_fwd_kernel<<<blocks, 256, 0, stream>>>(x_nchw, w_oihw, bias, a, out_f32, (bf16*)out_bf16, act_bf16);
+  return pg_check_launch("pg_conv_small_fwd");
+}
+
+extern "C" int pg_conv_small_bwd(const float* x_nchw, const float* w_oihw, const float* dy_pm, int N, int Cin, int H,
+                                 int W, int Cout, int kh, int kw, int pad_h, int pad_w, float* dw_oihw, float* dbias,
+                                 float* dx_nchw, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  PG_REQUIRE(x_nchw && w_oihw && dy_pm, "pg_conv_small_bwd: null argument");
+  ConvArgs a = {N, Cin, H, W, Cout, kh, kw, pad_h, pad_w, Cin * kh * kw};
+  PG_REQUIRE(a.K <= MAX_K, "pg_conv_small_bwd: Cin*kh*kw = %d exceeds %d", a.K, MAX_K);
+  const long long P = (long long)N * H * W;
+  if (dw_oihw) {
+    PG_REQUIRE(a.Cout * a.K <= WG_MAX_OUT_PER_THREAD * 256, "pg_conv_small_bwd: Cout*K = %d too large", a.Cout * a.K);
+    const size_t smem = (size_t)WG_PIX * (a.K + a.Cout) * sizeof(float);
+    PG_REQUIRE(smem <= 200 * 1024, "pg_conv_small_bwd: shared memory %zu too large", smem);
+    PG_CUDA(cudaFuncSetAttribute(conv_small_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    long long blocks = (P + WG_PIX - 1) / WG_PIX;
+    const long long cap = (long long)pg_num_sms() * 2;
+    if (blocks > cap) blocks = cap;
+    conv_small_wgrad_kernel<<<(unsigned)blocks, 256, smem, stream>>>(x_nchw, dy_pm, a, dw_oihw);
+    if (pg_check_launch("pg_conv_small_bwd(wgrad)")) return 1;
+  }
+  if (dbias) {
+    if (pg_colsum_f32(dy_pm, Cout, (int)P, Cout, dbias, 1, stream_)) return 1;
+  }
+  if (dx_nchw) {
+    const long long threads = P * 32;
+    conv_small_dgrad_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(w_oihw, dy_pm, a, dx_nchw);
+    if (pg_check_launch("pg_conv_small_bwd(dgrad)")) return 1;
+  }
+  return 0;
+}

@@ -1,0 +1,421 @@
+// pg_gemm.cu — the channel-contraction kernel: bf16 x bf16 -> fp32 on tcgen05 tensor cores.
+//
+// One persistent CTA per SM, warp-specialised:
+//   warp 0 (one lane)  TMA producer: global -> 128B-swizzled shared-memory stages, mbarrier expect_tx
+//   warp 1 (one lane)  MMA issuer:   tcgen05.mma cta_group::1, M=128, N=BN, K=16 per instruction,
+//                                    accumulator in TMEM (double buffered when 2*BN <= 512 columns)
+//   warp 2             TMEM allocator / deallocator
+//   warps 4..7         epilogue: tcgen05.ld (lane == output row) -> fused bias / act' / residual /
+//                                activation -> global stores (bf16 and/or fp32, or fp32 atomics for split-K)
+// Operand majors are template parameters so that forward (K,K), dgrad (K,MN) and wgrad (MN,MN) all read
+// the tensors where they lie: no transposed copies of activations or weights are ever materialised.
+//
+// Replaces: every 1x1 nn.Conv2d forward/backward on the reference path (see include/pg_b200.h).
+#include "../../include/pg_b200.h"
+#include "pg_common.cuh"
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle span
+constexpr int A_STAGE_BYTES = BM * BK * 2;
+
+struct GemmParams {
+  int M, N, K;
+  int num_m_blk, num_n_blk;
+  int k_iters;      // ceil(K / BK)
+  int k_per_split;  // k iterations per split
+  int splits;
+  int vec_ok;       // all epilogue pointers/pitches allow 16-byte vector access
+  pg_gemm_epilogue epi;
+};
+
+// ------------------------------------------------------------------------------------------------
+// Epilogue on one row segment: `vals` are 32 consecutive fp32 accumulator columns of output row `row`
+// starting at column `col0`; `ncols` (<= 32) of them are inside the matrix.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void epilogue_row32(const GemmParams& p, int row, int col0, int ncols, bool first_split,
+                                               const uint32_t (&acc)[32]) {
+  const pg_gemm_epilogue& e = p.epi;
+  float v[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]) * e.alpha;
+
+  const bool full = (ncols == 32) && p.vec_ok;
+  if (first_split && e.bias) {
+    if (full) {
+      const float4* b4 = reinterpret_cast<const float4*>(e.bias + col0);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float4 b = __ldg(b4 + i);
+        v[4 * i + 0] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+      }
+    } else {
+      for (int i = 0; i < ncols; ++i) v[i] += __ldg(e.bias + col0 + i);
+    }
+  }
+  if (e.dact != PG_ACT_NONE) {
+    const bf16* aux = reinterpret_cast<const bf16*>(e.aux) + (size_t)row * e.ld_aux + col0;
+    if (full) {
+      const uint4* a4 = reinterpret_cast<const uint4*>(aux);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint4 a = __ldg(a4 + i);
+        uint32_t w[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float2 f = unpack_bf16x2(w[j]);
+          v[8 * i + 2 * j] *= pg_act_bwd(e.dact, f.x);
+          v[8 * i + 2 * j + 1] *= pg_act_bwd(e.dact, f.y);
+        }
+      }
+    } else {
+      for (int i = 0; i < ncols; ++i) v[i] *= pg_act_bwd(e.dact, __bfloat162float(aux[i]));
+    }
+  }
+  if (first_split && e.res0) {
+    const float* r = e.res0 + (size_t)row * e.ld_res + col0;
+    if (full) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float4 b = __ldg(reinterpret_cast<const float4*>(r) + i);
+        v[4 * i + 0] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+      }
+    } else {
+      for (int i = 0; i < ncols; ++i) v[i] += r[i];
+    }
+  }
+  if (first_split && e.res1) {
+    const float* r = e.res1 + (size_t)row * e.ld_res + col0;
+    if (full) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float4 b = __ldg(reinterpret_cast<const float4*>(r) + i);
+        v[4 * i + 0] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+      }
+    } else {
+      for (int i = 0; i < ncols; ++i) v[i] += r[i];
+    }
+  }
+  if (e.out_f32) {
+    float* o = e.out_f32 + (size_t)row * e.ld_out_f32 + col0;
+    if (e.accumulate) {
+      for (int i = 0; i < ncols; ++i) atomicAdd(o + i, v[i]);
+    } else if (full) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        reinterpret_cast<float4*>(o)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    } else {
+      for (int i = 0; i < ncols; ++i) o[i] = v[i];
+    }
+  }
+  if (e.out_pre) {
+    bf16* o = reinterpret_cast<bf16*>(e.out_pre) + (size_t)row * e.ld_out_pre + col0;
+    if (full) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        reinterpret_cast<uint4*>(o)[i] =
+            make_uint4(pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
+                       pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
+    } else {
+      for (int i = 0; i < ncols; ++i) o[i] = __float2bfloat16(v[i]);
+    }
+  }
+  if (e.out_bf16) {
+    bf16* o = reinterpret_cast<bf16*>(e.out_bf16) + (size_t)row * e.ld_out_bf16 + col0;
+    if (e.act != PG_ACT_NONE) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = pg_act_fwd(e.act, v[i]);
+    }
+    if (full) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        reinterpret_cast<uint4*>(o)[i] =
+            make_uint4(pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
+                       pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
+    } else {
+      for (int i = 0; i < ncols; ++i) o[i] = __float2bfloat16(v[i]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// tcgen05 kernel
+// ------------------------------------------------------------------------------------------------
+template <int BN, int STAGES, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(256, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  constexpr int B_STAGE_BYTES = BN * BK * 2;
+  constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  constexpr int ACC_STAGES = (2 * BN <= 512) ? 2 : 1;
+  constexpr int TMEM_COLS = (ACC_STAGES * BN <= 32) ? 32
+                            : (ACC_STAGES * BN <= 64) ? 64
+                            : (ACC_STAGES * BN <= 128) ? 128
+                            : (ACC_STAGES * BN <= 256) ? 256 : 512;
+
+  extern __shared__ uint8_t smem_raw[];
+  // 128B swizzle atoms need 1024-byte aligned stage bases.
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + ACC_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + ACC_STAGES);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < ACC_STAGES; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+    fence_proxy_async_smem();
+  }
+  if (warp == 2) tmem_alloc<TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_tiles = p.num_m_blk * p.num_n_blk * p.splits;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== TMA producer =====================
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int n_blk = tile % p.num_n_blk;
+        const int rest = tile / p.num_n_blk;
+        const int m_blk = rest % p.num_m_blk;
+        const int ks = rest / p.num_m_blk;
+        const int k0 = ks * p.k_per_split;
+        const int k1 = min(k0 + p.k_per_split, p.k_iters);
+        for (int kit = k0; kit < k1; ++kit) {
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* sA = smem + s * STAGE_BYTES;
+          uint8_t* sB = sA + A_STAGE_BYTES;
+          mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+          if (!A_MN) {
+            tma_load_2d(sA, &tmA, &full_bar[s], kit * BK, m_blk * BM);  // box {64 k, 128 rows}
+          } else {
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j)  // box {64 m, 64 k-rows} per 64-wide MN atom
+              tma_load_2d(sA + j * (BK * 128), &tmA, &full_bar[s], m_blk * BM + j * 64, kit * BK);
+          }
+          if (!B_MN) {
+            tma_load_2d(sB, &tmB, &full_bar[s], kit * BK, n_blk * BN);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+              tma_load_2d(sB + j * (BK * 128), &tmB, &full_bar[s], n_blk * BN + j * 64, kit * BK);
+          }
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===================== MMA issuer =====================
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      int s = 0;
+      uint32_t ph = 0;
+      int as = 0;
+      uint32_t aph = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int rest = tile / p.num_n_blk;
+        const int ks = rest / p.num_m_blk;
+        const int k0 = ks * p.k_per_split;
+        const int k1 = min(k0 + p.k_per_split, p.k_iters);
+        mbar_wait(&tempty_bar[as], aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kit = k0; kit < k1; ++kit) {
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
+          const uint32_t b_addr = a_addr + A_STAGE_BYTES;
+#pragma unroll
+          for (int kk = 0; kk < BK / 16; ++kk) {
+            // K-major: 16 elements = 32 bytes inside the swizzle span; rows are 128B apart, 8-row groups 1024B.
+            // MN-major: 16 k-rows of 128B = 2048 bytes; 64-wide MN atoms are BK*128 bytes apart (LBO).
+            const uint64_t a_desc = A_MN ? umma_desc_sw128(a_addr + kk * 2048, BK * 128, 1024)
+                                         : umma_desc_sw128(a_addr + kk * 32, 16, 1024);
+            const uint64_t b_desc = B_MN ? umma_desc_sw128(b_addr + kk * 2048, BK * 128, 1024)
+                                         : umma_desc_sw128(b_addr + kk * 32, 16, 1024);
+            umma_bf16_ss(d_tmem, a_desc, b_desc, idesc, (kit > k0 || kk > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs have read it
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+        umma_commit(&tfull_bar[as]);  // accumulator complete -> epilogue
+        if (++as == ACC_STAGES) { as = 0; aph ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int ew = warp - 4;  // == warp % 4 -> TMEM lanes [32*ew, 32*ew+32)
+    int as = 0;
+    uint32_t aph = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int n_blk = tile % p.num_n_blk;
+      const int rest = tile / p.num_n_blk;
+      const int m_blk = rest % p.num_m_blk;
+      const int ks = rest / p.num_m_blk;
+      mbar_wait(&tfull_bar[as], aph);
+      tc_fence_after();
+      const int row = m_blk * BM + ew * 32 + lane;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t acc[32];
+        tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * BN + c * 32, acc);
+        tmem_wait_ld();
+        const int col0 = n_blk * BN + c * 32;
+        if (row < p.M && col0 < p.N) epilogue_row32(p, row, col0, min(32, p.N - col0), ks == 0, acc);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      if (++as == ACC_STAGES) { as = 0; aph ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// SIMT cross-check kernel (tests only): one thread per 1x32 output segment, same epilogue code.
+// ------------------------------------------------------------------------------------------------
+__global__ void gemm_simt_kernel(const bf16* __restrict__ A, int a_mn, int64_t lda, const bf16* __restrict__ B,
+                                 int b_mn, int64_t ldb, const GemmParams p) {
+  const int nseg = (p.N + 31) / 32;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)p.M * nseg) return;
+  const int row = (int)(idx / nseg);
+  const int col0 = (int)(idx % nseg) * 32;
+  const int ncols = min(32, p.N - col0);
+  float acc[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+  for (int k = 0; k < p.K; ++k) {
+    const float a = __bfloat162float(a_mn ? A[(size_t)k * lda + row] : A[(size_t)row * lda + k]);
+    for (int i = 0; i < ncols; ++i) {
+      const int n = col0 + i;
+      const float b = __bfloat162float(b_mn ? B[(size_t)k * ldb + n] : B[(size_t)n * ldb + k]);
+      acc[i] = fmaf(a, b, acc[i]);
+    }
+  }
+  uint32_t accu[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) accu[i] = __float_as_uint(acc[i]);
+  epilogue_row32(p, row, col0, ncols, true, accu);
+}
+
+template <int BN, int STAGES, bool A_MN, bool B_MN>
+int launch_tc(const void* A, int64_t lda, const void* B, int64_t ldb, GemmParams& p, cudaStream_t stream) {
+  CUtensorMap tmA, tmB;
+  if (!A_MN) {
+    if (pg_make_tmap_2d_bf16(&tmA, A, p.M, p.K, lda, BM, BK)) return 1;
+  } else {
+    if (pg_make_tmap_2d_bf16(&tmA, A, p.K, p.M, lda, BK, 64)) return 1;
+  }
+  if (!B_MN) {
+    if (pg_make_tmap_2d_bf16(&tmB, B, p.N, p.K, ldb, BN, BK)) return 1;
+  } else {
+    if (pg_make_tmap_2d_bf16(&tmB, B, p.K, p.N, ldb, BK, 64)) return 1;
+  }
+  constexpr int STAGE_BYTES = A_STAGE_BYTES + BN * BK * 2;
+  constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  auto kern = gemm_tc_kernel<BN, STAGES, A_MN, B_MN>;
+  PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+  const int num_tiles = p.num_m_blk * p.num_n_blk * p.splits;
+  const int grid = min(num_tiles, pg_num_sms());
+  kern<<<grid, 256, SMEM, stream>>>(tmA, tmB, p);
+  return pg_check_launch("pg_gemm_bf16(tcgen05)");
+}
+
+template <bool A_MN, bool B_MN>
+int dispatch_bn(const void* A, int64_t lda, const void* B, int64_t ldb, GemmParams& p, cudaStream_t stream) {
+  // Tile width: 256 when N is wide enough to fill it, otherwise the smallest of {32,64,128} covering N.
+  int bn;
+  if (p.N > 128) bn = 256;
+  else if (p.N > 64) bn = 128;
+  else if (p.N > 32) bn = 64;
+  else bn = 32;
+  if (B_MN && bn < 64) bn = 64;  // MN-major operands are staged in 64-wide swizzle atoms
+  // Narrow problems with few row blocks prefer 128 to create more tiles.
+  if (bn == 256 && ((p.M + BM - 1) / BM) * ((p.N + 255) / 256) * p.splits < pg_num_sms() && p.N % 256 != 0) bn = 128;
+  p.num_n_blk = (p.N + bn - 1) / bn;
+  switch (bn) {
+    case 256: return launch_tc<256, 4, A_MN, B_MN>(A, lda, B, ldb, p, stream);
+    case 128: return launch_tc<128, 6, A_MN, B_MN>(A, lda, B, ldb, p, stream);
+    case 64: return launch_tc<64, 8, A_MN, B_MN>(A, lda, B, ldb, p, stream);
+    default: return launch_tc<32, 8, A_MN, B_MN>(A, lda, B, ldb, p, stream);
+  }
+}
+
+}  // namespace
+
+extern "C" int pg_gemm_bf16(const void* A, int a_mn_major, int64_t lda, const void* B, int b_mn_major, int64_t ldb,
+                            int M, int N, int K, int split_k, const pg_gemm_epilogue* epi, int impl, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  PG_REQUIRE(A && B && epi, "pg_gemm_bf16: null operand");
+  PG_REQUIRE(M > 0 && N > 0 && K > 0, "pg_gemm_bf16: empty problem M=%d N=%d K=%d", M, N, K);
+  PG_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "pg_gemm_bf16: pitches must be multiples of 8 elements (lda=%lld ldb=%lld)",
+             (long long)lda, (long long)ldb);
+  PG_REQUIRE(epi->out_bf16 || epi->out_pre || epi->out_f32, "pg_gemm_bf16: no output requested");
+  PG_REQUIRE(epi->dact == PG_ACT_NONE || epi->aux, "pg_gemm_bf16: dact needs aux");
+  if (split_k < 1) split_k = 1;
+  if (split_k > 1)
+    PG_REQUIRE(epi->accumulate && epi->out_f32 && !epi->out_bf16 && !epi->out_pre && epi->dact == PG_ACT_NONE,
+               "pg_gemm_bf16: split_k > 1 requires accumulate=1 into out_f32 only");
+  GemmParams p;
+  p.M = M; p.N = N; p.K = K;
+  p.num_m_blk = (M + BM - 1) / BM;
+  p.num_n_blk = 0;
+  p.k_iters = (K + BK - 1) / BK;
+  if (split_k > p.k_iters) split_k = p.k_iters;
+  p.k_per_split = (p.k_iters + split_k - 1) / split_k;
+  p.splits = (p.k_iters + p.k_per_split - 1) / p.k_per_split;  // no empty split
+  p.epi = *epi;
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  p.vec_ok = 1;
+  if (epi->bias && !al16(epi->bias)) p.vec_ok = 0;
+  if (epi->aux && (!al16(epi->aux) || epi->ld_aux % 8)) p.vec_ok = 0;
+  if (epi->res0 && (!al16(epi->res0) || epi->ld_res % 4)) p.vec_ok = 0;
+  if (epi->res1 && (!al16(epi->res1) || epi->ld_res % 4)) p.vec_ok = 0;
+  if (epi->out_f32 && (!al16(epi->out_f32) || epi->ld_out_f32 % 4)) p.vec_ok = 0;
+  if (epi->out_pre && (!al16(epi->out_pre) || epi->ld_out_pre % 8)) p.vec_ok = 0;
+  if (epi->out_bf16 && (!al16(epi->out_bf16) || epi->ld_out_bf16 % 8)) p.vec_ok = 0;
+
+  if (impl == 1) {
+    p.splits = 1;
+    p.k_per_split = p.k_iters;
+    const int nseg = (N + 31) / 32;
+    const long long total = (long long)M * nseg;
+    const int threads = 128;
+    const long long blocks = (total + threads - 1) / threads;
+    gemm_simt_kernel<<<(unsigned)blocks, threads, 0, stream>>>(reinterpret_cast<const bf16*>(A), a_mn_major, lda,
+                                                                 reinterpret_cast<const bf16*>(B), b_mn_major, ldb, p);
+    return pg_check_launch("pg_gemm_bf16(simt)");
+  }
+  if (!a_mn_major && !b_mn_major) return dispatch_bn<false, false>(A, lda, B, ldb, p, stream);
+  if (!a_mn_major && b_mn_major) return dispatch_bn<false, true>(A, lda, B, ldb, p, stream);
+  if (a_mn_major && b_mn_major) return dispatch_bn<true, true>(A, lda, B, ldb, p, stream);
+  return dispatch_bn<true, false>(A, lda, B, ldb, p, stream);
+}
