@@ -10,6 +10,10 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
+# The torch restatements are the fp32 yardstick: no TF32 shortcuts in cuDNN/cuBLAS.
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+
 
 @pytest.fixture(scope="module")
 def L():
