@@ -1,0 +1,309 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark: images/sec of one ImageGPT CIFAR-10-shaped training step.
+
+A "step" is the reference's `Trainer._train_one_batch` (reference trainer.py:173-193) on one synthetic batch:
+zero_grad -> forward -> BCE loss -> backward (+ DDP gradient all-reduce when N > 1) ->
+clip_grad_norm_(params, 1e50) -> Adam step -> MultiplicativeLR step -> loss.item(), norm.item().
+
+    python bench.py [--gpus N --steps K --warmup W]            our arm (N>1: launched by torch.distributed.run)
+    python bench.py --impl reference [...]                      the reference's CPU path (oracle port), rank 0 only
+
+One JSON line on stdout (rank 0).  `value` has the batch resident in HBM when the timed region starts; `e2e`
+goes through the public Module API with the batch in pinned host memory (H2D copy + loss/grad-norm D2H read
+inside the timed region).  `roofline` is for the dominant kernel (the tcgen05 channel-contraction GEMM), timed
+with CUDA events around every launch inside the timed region.  `cpu_baseline` is the oracle port on the host
+cores on a bounded sample (rank 0, N=1 only).
+"""
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    # BASELINE.json configs[4] — the configuration the metric is quoted on (fits one GPU)
+    "c5": dict(name="ImageGPT 3x32x32 CIFAR-10-shaped, 24 blocks / 8 heads / 512 ch",
+               cfg=dict(in_channels=3, out_channels=3, in_size=32, n_transformer_blocks=24, n_attention_heads=8,
+                        n_embedding_channels=512),
+               shape=(3, 32, 32), batch=64, lr=5e-3, algo_gflop_per_img=541.289, cpu_batch=2),
+    # BASELINE.json configs[1]
+    "c2": dict(name="ImageGPT 1x28x28 MNIST-shaped, 8 blocks / 4 heads / 64 ch",
+               cfg=dict(in_channels=1, out_channels=1, in_size=28, n_transformer_blocks=8, n_attention_heads=4,
+                        n_embedding_channels=64),
+               shape=(1, 28, 28), batch=64, lr=5e-3, algo_gflop_per_img=3.742, cpu_batch=16),
+}
+
+
+def synthetic_batch(n, shape, seed):
+    """CIFAR-shaped: uint8/255 like ToTensor (reference datasets.py:170); MNIST-shaped: Bernoulli(0.5)."""
+    g = torch.Generator().manual_seed(seed)
+    if shape[0] == 1:
+        return torch.bernoulli(torch.full((n, *shape), 0.5), generator=g)
+    return torch.randint(0, 256, (n, *shape), generator=g).float() / 255
+
+
+def recipe_loss(x, _, preds):
+    """loss_fn of the reference recipes (image_gpt.py:158-162)."""
+    b = x.shape[0]
+    x, preds = x.reshape(b, -1), preds.reshape(b, -1)
+    loss = torch.nn.functional.binary_cross_entropy_with_logits(preds, x, reduction="none")
+    return loss.sum(dim=1).mean()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm_gbs=p["hbm_gbs"], tf_burst=p["bf16_tflops"], tf_sustained=p["bf16_tflops_sustained"],
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        reasons = []
+        for name, col in (("hw_slowdown", 3), ("hw_thermal_slowdown", 4), ("sw_thermal_slowdown", 5), ("sw_power_cap", 6)):
+            if any(len(r) > col and r[col].lower().startswith("active") for r in self.rows):
+                reasons.append(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(float(self.rows[0][1])), "reasons": reasons,
+                "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------
+# Our arm
+# --------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+
+    from pytorch_generative_b200 import _lib as L
+    from pytorch_generative_b200 import models
+
+    spec = CONFIGS[args.config]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            sys.exit("bench.py --gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    L.load()
+
+    batch = args.batch or spec["batch"]
+    torch.manual_seed(0)
+    model = models.ImageGPT(**spec["cfg"]).to(dev)
+    train_model = model
+    if world > 1:
+        train_model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], output_device=local_rank,
+                                                                broadcast_buffers=False, gradient_as_bucket_view=True)
+    params = [p for p in model.parameters()]
+    opt = torch.optim.Adam(params, lr=spec["lr"])
+    sched = torch.optim.lr_scheduler.MultiplicativeLR(opt, lr_lambda=lambda _: 0.999977)
+    x_host = synthetic_batch(batch, spec["shape"], seed=rank).pin_memory()  # rank r uses seed r
+    x_dev = x_host.to(dev)
+
+    def step(x):
+        train_model.train()
+        opt.zero_grad()
+        preds = train_model(x)
+        loss = recipe_loss(x, None, preds)
+        loss.backward()
+        norm = torch.nn.utils.clip_grad_norm_(params, 1e50)
+        opt.step()
+        sched.step()
+        return loss.item(), norm.item()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        last = None
+        for _ in range(steps):
+            last = fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item(), last
+
+    for _ in range(max(args.warmup, 3)):
+        step(x_dev)
+
+    # ---- device-resident timing, with per-GEMM CUDA events for the roofline line ----
+    gemm_events = []
+    L.gemm_timing_hook = lambda flops, a, b: gemm_events.append((flops, a, b))
+    launches0 = L.launch_count()
+    with ClockSampler(local_rank) as clocks:
+        ms_total, last = timed(lambda: step(x_dev), args.steps)
+    launches = L.launch_count() - launches0
+    L.gemm_timing_hook = None
+    gemm_ms = sum(a.elapsed_time(b) for _, a, b in gemm_events)
+    gemm_flops = sum(f for f, _, _ in gemm_events)
+
+    # ---- end-to-end: pinned host batch -> H2D -> step -> D2H scalars, through the Module API ----
+    def e2e_step():
+        return step(x_host.to(dev, non_blocking=True))
+
+    e2e_step()
+    ms_e2e, _ = timed(e2e_step, args.steps)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    ms_step = ms_total / args.steps
+    imgs = batch * world
+    value = imgs / (ms_step / 1e3)
+    e2e_value = imgs / (ms_e2e / args.steps / 1e3)
+    achieved_tf = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
+    n_gemm = len(gemm_events)
+    out = {
+        "metric": "images/sec training step (ImageGPT CIFAR-10 32x32)", "value": round(value, 2), "unit": "images/sec",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": spec["name"] + f", per-GPU batch {batch}, Adam lr {spec['lr']}, fp32 master weights, "
+                   "bf16 tensor-core operands, fp32 residual stream", "global_batch": imgs, "parallelism": f"dp{world}",
+                   "l2": "working set per step (~29 GB of activations at batch 64) >> 126 MB L2; no explicit flush needed",
+                   "baseline_config": "BASELINE.json configs[4] (the metric's configuration)"},
+        "e2e": {"value": round(e2e_value, 2), "unit": "images/sec", "h2d_bytes_per_step": x_host.numel() * 4,
+                "d2h_bytes_per_step": 8},
+        "gpu_launches": int(launches),
+        "clocks": clocks.summary(),
+        "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (pg_gemm_bf16, tcgen05 1x1-conv fwd/dgrad/wgrad)",
+                     "achieved": round(achieved_tf, 1), "peak": pk["tf_sustained"], "unit": "TFLOP/s",
+                     "frac": round(achieved_tf / pk["tf_sustained"], 4), "traffic": None,
+                     "launches_timed": n_gemm, "share_of_step": round(gemm_ms / ms_total, 4), "peak_source": pk["source"],
+                     "step_algo_tflops": round(spec["algo_gflop_per_img"] * value / world / 1e3, 1),
+                     "step_frac_of_peak": round(spec["algo_gflop_per_img"] * value / world / 1e3 / pk["tf_sustained"], 4)},
+        "last_loss": last[0], "last_grad_norm": last[1],
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(spec, steps=2, warmup=1)
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# --------------------------------------------------------------------------------------------------
+# Reference arm / cpu_baseline: the oracle port of the reference's CPU path on the host cores
+# --------------------------------------------------------------------------------------------------
+def _oracle_state(spec):
+    """Reference-default init of the same architecture.  Built from our Module (identical parameter names,
+    shapes and torch default initialisers as the reference constructors); weights are only a starting point for
+    timing."""
+    from pytorch_generative_b200 import models
+
+    torch.manual_seed(0)
+    m = models.ImageGPT(**spec["cfg"])
+    return {k: v.detach().clone() for k, v in m.state_dict().items()}
+
+
+def cpu_baseline(spec, steps, warmup):
+    from oracle import reference_path as O
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    nb = spec["cpu_batch"]
+    ts = O.TrainState("image_gpt", _oracle_state(spec), spec["cfg"], lr=spec["lr"])
+    x = synthetic_batch(nb, spec["shape"], seed=0)
+    for _ in range(warmup):
+        ts.step(x)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        ts.step(x)
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": round(nb / dt, 4), "unit": "images/sec", "cores": torch.get_num_threads(), "kind": "port",
+            "ms_per_step": round(dt * 1e3, 1),
+            "sample": f"{steps} timed steps (+{warmup} warm-up) of the same training step at batch {nb} on the host CPU "
+                      "(oracle/reference_path.py, fp32, torch CPU ops as the reference)"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    spec = CONFIGS[args.config]
+    steps = min(args.steps, 3)
+    cb = cpu_baseline(spec, steps=steps, warmup=1)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    out = {
+        "impl": "reference", "metric": "images/sec training step (ImageGPT CIFAR-10 32x32)", "value": cb["value"],
+        "unit": "images/sec", "n_gpus": world, "steps": steps, "warmup": 1, "ms_per_step": cb["ms_per_step"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": spec["name"] + f", CPU batch {spec['cpu_batch']} (bounded sample)", "parallelism": "cpu"},
+        "cpu_baseline": cb,
+        "e2e": {"value": cb["value"], "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c5", choices=sorted(CONFIGS))
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the recipe's)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

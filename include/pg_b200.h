@@ -29,6 +29,8 @@ int pg_abi_version(void);
 const char* pg_last_error(void);
 /* Number of SMs of the current device (148 on B200); used by callers to size split-K. */
 int pg_sm_count(void);
+/* Number of kernels this library has launched in this process (all threads); bench.py's gpu_launches. */
+unsigned long long pg_launch_count(void);
 
 /* Activation ids (shared by the GEMM epilogue and the elementwise kernels). */
 enum { PG_ACT_NONE = 0, PG_ACT_RELU = 1, PG_ACT_GELU = 2, PG_ACT_ELU = 3, PG_ACT_TANH = 4 };
@@ -126,17 +128,22 @@ int pg_cast_f32_to_bf16(const float* x, void* y, int64_t numel, void* stream);
  * re-zero, attn@v, head concat).  q/k/v/o are pixel-major bf16 with per-image sequences of length S
  * (seq index = row*W+col), heads are contiguous channel blocks of dk (q,k) / dv (v,o) channels.
  * strict=1 is mask_center=True (position i attends j<i; row 0 yields zeros), strict=0 attends j<=i.
- * scale = 1/sqrt(dk).  lse [N, H, S] fp32 (log-sum-exp of scaled scores; -inf rows store 0 with o=0).
- * impl: 0 = tcgen05 kernel, 1 = SIMT cross-check.
+ * `scale` multiplies q.k (the reference uses 1/sqrt(embed_channels/n_heads); it is passed explicitly so
+ * that head slots may be zero-padded: the tcgen05 kernels require dk == 64 and dv in {64, 128}, narrower
+ * heads are laid out in 64-wide slots whose extra columns are zero).
+ * lse [N, H, S] fp32 (log-sum-exp of scaled scores; rows without keys store 0 and o = 0).
+ * impl: 0 = tcgen05 kernel, 1 = SIMT cross-check (any dk, dv <= 128, S <= 1024).
  * ------------------------------------------------------------------------------------------- */
 int pg_causal_attn_fwd(const void* q, int64_t ld_q, const void* k, int64_t ld_k, const void* v, int64_t ld_v,
-                       void* o, int64_t ld_o, float* lse, int N, int S, int H, int dk, int dv, int strict,
-                       int impl, void* stream);
-/* delta scratch: [N, H, S] fp32.  dq/dk/dv are bf16 pixel-major with the given pitches. */
+                       void* o, int64_t ld_o, float* lse, int N, int S, int H, int dk, int dv, float scale,
+                       int strict, int impl, void* stream);
+/* Scratch: delta [N, H, S] fp32; dq_accum [N*S, H*dk] fp32, zero-filled by the caller (impl 0 only: dQ is
+ * accumulated across key tiles with fp32 atomics, then rounded to bf16).  dq/dk/dv are bf16 pixel-major. */
 int pg_causal_attn_bwd(const void* q, int64_t ld_q, const void* k, int64_t ld_k, const void* v, int64_t ld_v,
                        const void* o, int64_t ld_o, const void* d_o, int64_t ld_do, const float* lse,
-                       float* delta, void* dq, int64_t ld_dq, void* dk_, int64_t ld_dk, void* dv_,
-                       int64_t ld_dv, int N, int S, int H, int dk, int dv, int strict, int impl, void* stream);
+                       float* delta, float* dq_accum, void* dq, int64_t ld_dq, void* dk_, int64_t ld_dk,
+                       void* dv_, int64_t ld_dv, int N, int S, int H, int dk, int dv, float scale, int strict,
+                       int impl, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Tap-list convolution for small channel counts (CausalConv2d input layers, Cin in {1,3}):

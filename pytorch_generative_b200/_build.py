@@ -17,7 +17,9 @@ INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 LIB_PATH = os.path.join(_HERE, "libpg_b200.so")
 
 SOURCES = ["pg_host.cu", "pg_gemm.cu", "pg_elementwise.cu", "pg_attention.cu", "pg_conv.cu"]
-HEADERS = [os.path.join(CSRC, "pg_common.cuh"), os.path.join(INCLUDE, "pg_b200.h")]
+import glob
+
+HEADERS = sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + [os.path.join(INCLUDE, "pg_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

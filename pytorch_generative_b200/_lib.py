@@ -8,6 +8,7 @@ are not CUDA tensors, the call raises.
 """
 
 import ctypes
+import math
 import os
 
 import torch
@@ -45,13 +46,13 @@ _SIGNATURES = {
     "pg_nchw_to_pm": [_vp, _i32, _i32, _i32, _vp, _i32, _i64, _vp],
     "pg_pm_to_nchw": [_vp, _i32, _i64, _i32, _i32, _i32, _vp, _vp],
     "pg_cast_f32_to_bf16": [_vp, _vp, _i64, _vp],
-    "pg_causal_attn_fwd": [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
-    "pg_causal_attn_bwd": [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _vp,
-                           _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
+    "pg_causal_attn_fwd": [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _i32, _i32, _vp],
+    "pg_causal_attn_bwd": [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _i64,
+                           _vp, _i64, _i32, _i32, _i32, _i32, _i32, _f32, _i32, _i32, _vp],
     "pg_conv_small_fwd": [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp],
     "pg_conv_small_bwd": [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp],
 }
-EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + ["pg_abi_version", "pg_last_error", "pg_sm_count"])
+EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + ["pg_abi_version", "pg_last_error", "pg_sm_count", "pg_launch_count"])
 
 _lib = None
 
@@ -73,6 +74,8 @@ def load():
     lib.pg_abi_version.argtypes = []
     lib.pg_sm_count.restype = ctypes.c_int
     lib.pg_sm_count.argtypes = []
+    lib.pg_launch_count.restype = ctypes.c_ulonglong
+    lib.pg_launch_count.argtypes = []
     for name, argtypes in _SIGNATURES.items():
         fn = getattr(lib, name)
         fn.argtypes = argtypes
@@ -105,6 +108,15 @@ def _pm(t):
     assert t.dim() == 2 and t.stride(1) == 1, f"expected a [P, C] matrix with unit inner stride, got {t.shape} {t.stride()}"
     return _ptr(t), t.stride(0)
 
+
+def launch_count():
+    """Kernels launched by libpg_b200.so so far in this process."""
+    return int(load().pg_launch_count())
+
+
+# Optional per-call timing hook used by bench.py: when set, gemm() brackets its launch with CUDA events on
+# the launching stream and reports (flops, start_event, end_event).
+gemm_timing_hook = None
 
 _sm_count = None
 
@@ -151,8 +163,15 @@ def gemm(A, B, M, N, K, *, a_mn=False, b_mn=False, bias=None, aux=None, dact=ACT
         assert out_f32.dtype == torch.float32 and out_f32.shape[0] >= M
         e.out_f32, e.ld_out_f32 = _pm(out_f32)
     e.act, e.dact, e.accumulate, e.alpha = act, dact, int(accumulate), alpha
+    hook = gemm_timing_hook
+    if hook is not None:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
     _check(lib.pg_gemm_bf16(a_ptr, int(a_mn), lda, b_ptr, int(b_mn), ldb, M, N, K, split_k, ctypes.byref(e), impl,
                             _stream()), "pg_gemm_bf16")
+    if hook is not None:
+        ev1.record()
+        hook(2.0 * M * N * K, ev0, ev1)
 
 
 def colsum(x, out, accumulate=False):
@@ -238,20 +257,23 @@ def cast_bf16(x, y):
 # ------------------------------------------------------------------------------------------------
 # Attention / small conv
 # ------------------------------------------------------------------------------------------------
-def causal_attn_fwd(q, k, v, o, lse, N, S, H, dk, dv, strict, impl=0):
+def causal_attn_fwd(q, k, v, o, lse, N, S, H, dk, dv, strict, impl=0, dk_true=None):
+    """dk is the column width of a head slot; dk_true (default dk) sets the 1/sqrt(dk) scale."""
     lib = load()
     (qp, ldq), (kp, ldk), (vp, ldv), (op, ldo) = _pm(q), _pm(k), _pm(v), _pm(o)
-    _check(lib.pg_causal_attn_fwd(qp, ldq, kp, ldk, vp, ldv, op, ldo, _ptr(lse), N, S, H, dk, dv, int(strict), impl,
-                                  _stream()), "pg_causal_attn_fwd")
+    scale = 1.0 / math.sqrt(dk_true or dk)
+    _check(lib.pg_causal_attn_fwd(qp, ldq, kp, ldk, vp, ldv, op, ldo, _ptr(lse), N, S, H, dk, dv, scale, int(strict),
+                                  impl, _stream()), "pg_causal_attn_fwd")
 
 
-def causal_attn_bwd(q, k, v, o, do, lse, delta, dq, dk_, dv_, N, S, H, dk, dv, strict, impl=0):
+def causal_attn_bwd(q, k, v, o, do, lse, delta, dq_accum, dq, dk_, dv_, N, S, H, dk, dv, strict, impl=0, dk_true=None):
     lib = load()
     (qp, ldq), (kp, ldk), (vp, ldv), (op, ldo), (dop, lddo) = _pm(q), _pm(k), _pm(v), _pm(o), _pm(do)
     (dqp, lddq), (dkp, lddk), (dvp, lddv) = _pm(dq), _pm(dk_), _pm(dv_)
-    _check(lib.pg_causal_attn_bwd(qp, ldq, kp, ldk, vp, ldv, op, ldo, dop, lddo, _ptr(lse), _ptr(delta), dqp, lddq,
-                                  dkp, lddk, dvp, lddv, N, S, H, dk, dv, int(strict), impl, _stream()),
-           "pg_causal_attn_bwd")
+    scale = 1.0 / math.sqrt(dk_true or dk)
+    _check(lib.pg_causal_attn_bwd(qp, ldq, kp, ldk, vp, ldv, op, ldo, dop, lddo, _ptr(lse), _ptr(delta),
+                                  _ptr(dq_accum), dqp, lddq, dkp, lddk, dvp, lddv, N, S, H, dk, dv, scale, int(strict),
+                                  impl, _stream()), "pg_causal_attn_bwd")
 
 
 def conv_small_fwd(x, w, bias, pad, out_f32=None, out_bf16=None, act_bf16=ACT_NONE):

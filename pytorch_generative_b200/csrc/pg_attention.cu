@@ -22,6 +22,7 @@ struct AttnArgs {
   float* lse;
   const float* lse_in;
   float* delta;
+  float* dq_accum;
   int N, S, H, dk, dv, strict;
   float scale;
 };
@@ -175,7 +176,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_simt(const AttnArgs a) {
 
 extern "C" int pg_causal_attn_fwd(const void* q, int64_t ld_q, const void* k, int64_t ld_k, const void* v,
                                   int64_t ld_v, void* o, int64_t ld_o, float* lse, int N, int S, int H, int dk,
-                                  int dv, int strict, int impl, void* stream_) {
+                                  int dv, float scale, int strict, int impl, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   PG_REQUIRE(q && k && v && o && lse, "pg_causal_attn_fwd: null argument");
   PG_REQUIRE(N > 0 && S > 0 && H > 0 && dk > 0 && dv > 0, "pg_causal_attn_fwd: empty problem");
@@ -184,7 +185,7 @@ extern "C" int pg_causal_attn_fwd(const void* q, int64_t ld_q, const void* k, in
   a.ld_q = ld_q; a.ld_k = ld_k; a.ld_v = ld_v; a.ld_o = ld_o;
   a.lse = lse;
   a.N = N; a.S = S; a.H = H; a.dk = dk; a.dv = dv; a.strict = strict;
-  a.scale = 1.0f / sqrtf((float)dk);
+  a.scale = scale;
   if (impl == 1) {
     PG_REQUIRE(S <= MAX_S && dk <= MAX_D && dv <= MAX_D, "pg_causal_attn_fwd(simt): S<=%d, d<=%d", MAX_S, MAX_D);
     const long long total = (long long)N * H * S;
@@ -197,9 +198,9 @@ extern "C" int pg_causal_attn_fwd(const void* q, int64_t ld_q, const void* k, in
 
 extern "C" int pg_causal_attn_bwd(const void* q, int64_t ld_q, const void* k, int64_t ld_k, const void* v,
                                   int64_t ld_v, const void* o, int64_t ld_o, const void* d_o, int64_t ld_do,
-                                  const float* lse, float* delta, void* dq, int64_t ld_dq, void* dk_, int64_t ld_dk,
-                                  void* dv_, int64_t ld_dv, int N, int S, int H, int dk, int dv, int strict, int impl,
-                                  void* stream_) {
+                                  const float* lse, float* delta, float* dq_accum, void* dq, int64_t ld_dq, void* dk_,
+                                  int64_t ld_dk, void* dv_, int64_t ld_dv, int N, int S, int H, int dk, int dv,
+                                  float scale, int strict, int impl, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   PG_REQUIRE(q && k && v && o && d_o && lse && delta && dq && dk_ && dv_, "pg_causal_attn_bwd: null argument");
   PG_REQUIRE(N > 0 && S > 0 && H > 0 && dk > 0 && dv > 0, "pg_causal_attn_bwd: empty problem");
@@ -210,7 +211,8 @@ extern "C" int pg_causal_attn_bwd(const void* q, int64_t ld_q, const void* k, in
   a.ld_dq = ld_dq; a.ld_dk = ld_dk; a.ld_dv = ld_dv;
   a.lse_in = lse; a.delta = delta;
   a.N = N; a.S = S; a.H = H; a.dk = dk; a.dv = dv; a.strict = strict;
-  a.scale = 1.0f / sqrtf((float)dk);
+  a.scale = scale;
+  a.dq_accum = dq_accum;
   const long long total = (long long)N * H * S;
   attn_delta_kernel<<<(unsigned)((total * 32 + 255) / 256), 256, 0, stream>>>(a);
   if (pg_check_launch("pg_causal_attn_bwd(delta)")) return 1;

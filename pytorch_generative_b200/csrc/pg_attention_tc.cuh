@@ -1,12 +1,532 @@
-// pg_attention_tc.cuh — tensor-core causal attention (placeholder until the tcgen05 kernels land).
+// pg_attention_tc.cuh — causal attention on tcgen05 tensor cores (included by pg_attention.cu).
+//
+// Head slots are 64 columns wide for q/k (dk == 64, narrower heads are zero padded by the caller) and 64 or
+// 128 wide for v/o.  Tiles are 128 queries x 128 keys; all operands arrive by TMA (3-D maps [N][S][cols], so rows
+// past the end of an image are zero-filled) into 128B-swizzled shared memory and are read in place by
+// tcgen05.mma under two views of the same bytes: a [rows][64-col swizzle atom] tile is a K-major operand
+// with K along the columns, or an MN-major operand with K along the rows.
+//
+// Forward, one CTA per (image, head, 128-query tile), 2 CTAs co-resident per SM (DV = 64):
+//   warp 4   TMA producer (Q once, K/V ring of 2)
+//   warp 5   TMEM allocator + MMA issuer:  S = Q K^T (TMEM cols [0,128)),  PV = P V (cols [128,128+DV))
+//   warps 0-3 one query row per thread: two passes over S in TMEM (max, then exp2 + sum), P (bf16) to smem,
+//            running output kept in registers: O = O * alpha + PV.
+// Backward, one CTA per (image, head, 128-key tile), looping over query tiles i >= j:
+//   S = Q_i K_j^T, dP = dO_i V_j^T -> P = exp2(S*c - lse), dS = P * (dP - delta) (bf16 to smem) ->
+//   dV_j += P^T dO_i, dK_j += dS^T Q_i (accumulated in TMEM), dQ_i = dS K_j (fp32 atomics into dq_accum).
 #pragma once
+
 namespace {
-int attn_fwd_tc(const AttnArgs&, cudaStream_t) {
-  pg_set_error("pg_causal_attn_fwd: tcgen05 kernel not built yet");
-  return 1;
+
+constexpr int AT = 128;              // tile edge (queries and keys)
+constexpr int ATOM_BYTES = AT * 128; // one 64-column swizzle atom of a 128-row tile
+
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
-int attn_bwd_tc(const AttnArgs&, cudaStream_t) {
-  pg_set_error("pg_causal_attn_bwd: tcgen05 kernel not built yet");
-  return 1;
+
+// Row r of a [128 x 128] bf16 tile stored as 2 atoms x [128 rows][128 B] with the TMA 128B swizzle:
+// writes 32 consecutive elements (chunk c of 4) given as 16 packed bf16x2 words.
+__device__ __forceinline__ void store_tile_row_chunk(uint8_t* tile, int r, int c, const uint32_t (&w)[16]) {
+  uint8_t* row = tile + (c >> 1) * ATOM_BYTES + r * 128;
+  const int unit0 = (c & 1) * 4;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int uidx = (unit0 + u) ^ (r & 7);
+    *reinterpret_cast<uint4*>(row + uidx * 16) = make_uint4(w[4 * u], w[4 * u + 1], w[4 * u + 2], w[4 * u + 3]);
+  }
 }
+
+// Descriptors for the two views of a tile whose atoms are ATOM_BYTES apart.
+// K-major view: K runs along the 64 columns of an atom (then to the next atom); kk = index of the 16-wide K step.
+__device__ __forceinline__ uint64_t desc_kmajor(uint32_t tile_addr, int kk) {
+  return umma_desc_sw128(tile_addr + (kk >> 2) * ATOM_BYTES + (kk & 3) * 32, 16, 1024);
+}
+// MN-major view: K runs along the rows (16 rows = 2048 B per K step); MN atoms are ATOM_BYTES apart.
+__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t tile_addr, int kk) {
+  return umma_desc_sw128(tile_addr + kk * 2048, ATOM_BYTES, 1024);
+}
+
+struct AttnTmaps {
+  CUtensorMap q, k, v, d_o;
+};
+
+// ------------------------------------------------------------------------------------------------
+// Forward
+// ------------------------------------------------------------------------------------------------
+template <int DV>
+__global__ void __launch_bounds__(192, DV == 64 ? 2 : 1)
+attn_fwd_tc_kernel(const __grid_constant__ AttnTmaps tm, const AttnArgs a, const int T) {
+  constexpr int V_BYTES = DV * 256;
+  constexpr int TMEM_COLS = 256;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + ATOM_BYTES;          // 2 stages
+  uint8_t* sV = sK + 2 * ATOM_BYTES;      // 2 stages
+  uint8_t* sP = sV + 2 * V_BYTES;         // 2 atoms
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * ATOM_BYTES);
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = bars + 1;   // [2]
+  uint64_t* kv_empty = bars + 3;  // [2]
+  uint64_t* s_full = bars + 5;
+  uint64_t* p_full = bars + 6;
+  uint64_t* o_full = bars + 7;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nh = blockIdx.x % (a.N * a.H);
+  const int i = T - 1 - blockIdx.x / (a.N * a.H);  // longest rows first
+  const int n = nh / a.H, h = nh % a.H;
+  const int ntiles = i + 1;
+
+  if (threadIdx.x == 0) {
+    if (smem_u32(smem) & 1023u) { printf("pg attention: shared memory base not 1024B aligned\n"); __trap(); }
+    mbar_init(q_full, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 128);
+    mbar_init(o_full, 1);
+    fence_barrier_init();
+    fence_proxy_async_smem();
+  }
+  if (warp == 5) tmem_alloc<TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem_s = tmem, tmem_o = tmem + 128;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, ATOM_BYTES);
+      tma_load_3d(sQ, &tm.q, q_full, h * 64, i * AT, n);
+      for (int j = 0; j < ntiles; ++j) {
+        const int st = j & 1;
+        mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&kv_full[st], ATOM_BYTES + V_BYTES);
+        tma_load_3d(sK + st * ATOM_BYTES, &tm.k, &kv_full[st], h * 64, j * AT, n);
+#pragma unroll
+        for (int v = 0; v < DV / 64; ++v)
+          tma_load_3d(sV + st * V_BYTES + v * ATOM_BYTES, &tm.v, &kv_full[st], h * DV + v * 64, j * AT, n);
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t idesc_o = umma_idesc_bf16(128, DV, 0, 1);
+      const uint32_t q_addr = smem_u32(sQ), p_addr = smem_u32(sP);
+      mbar_wait(q_full, 0);
+      mbar_wait(&kv_full[0], 0);
+      tc_fence_after();
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk)
+        umma_bf16_ss(tmem_s, desc_kmajor(q_addr, kk), desc_kmajor(smem_u32(sK), kk), idesc_s, kk > 0);
+      umma_commit(s_full);
+      for (int j = 0; j < ntiles; ++j) {
+        const int st = j & 1;
+        mbar_wait(p_full, j & 1);
+        tc_fence_after();
+        const uint32_t v_addr = smem_u32(sV + st * V_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)
+          umma_bf16_ss(tmem_o, desc_kmajor(p_addr, kk), desc_mnmajor(v_addr, kk), idesc_o, kk > 0);
+        umma_commit(o_full);
+        umma_commit(&kv_empty[st]);
+        if (j + 1 < ntiles) {
+          const int sn = (j + 1) & 1;
+          mbar_wait(&kv_full[sn], ((j + 1) >> 1) & 1);
+          tc_fence_after();
+          const uint32_t k_addr = smem_u32(sK + sn * ATOM_BYTES);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            umma_bf16_ss(tmem_s, desc_kmajor(q_addr, kk), desc_kmajor(k_addr, kk), idesc_s, kk > 0);
+          umma_commit(s_full);
+        }
+      }
+    }
+  } else {
+    // ===================== softmax / output warps: thread == query row =====================
+    const int r = warp * 32 + lane;
+    const int qi = i * AT + r;
+    const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+    const float sl2 = a.scale * 1.4426950408889634f;
+    const int qlim = qi - a.strict;  // keys kj <= qlim are visible
+    float m = -INFINITY, l = 0.f;
+    float O[DV];
+#pragma unroll
+    for (int d = 0; d < DV; ++d) O[d] = 0.f;
+    for (int j = 0; j < ntiles; ++j) {
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      const bool diag = (j == i);
+      const int k0 = j * AT;
+      float mx = m;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_s + lane_base + c * 32, v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          float s = __uint_as_float(v[e]);
+          if (diag && (k0 + c * 32 + e > qlim)) s = -INFINITY;
+          mx = fmaxf(mx, s);
+        }
+      }
+      const float m_use = (mx == -INFINITY) ? 0.f : mx;
+      const float alpha = fast_exp2((m - m_use) * sl2);  // m = -inf -> 0
+      const float mb = m_use * sl2;
+      float lt = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_s + lane_base + c * 32, v);
+        tmem_wait_ld();
+        uint32_t w[16];
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) {
+          float p0 = fast_exp2(fmaf(__uint_as_float(v[e]), sl2, -mb));
+          float p1 = fast_exp2(fmaf(__uint_as_float(v[e + 1]), sl2, -mb));
+          if (diag) {
+            if (k0 + c * 32 + e > qlim) p0 = 0.f;
+            if (k0 + c * 32 + e + 1 > qlim) p1 = 0.f;
+          }
+          lt += p0 + p1;
+          w[e >> 1] = pack_bf16x2(p0, p1);
+        }
+        store_tile_row_chunk(sP, r, c, w);
+      }
+      fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      tc_fence_before();
+      mbar_arrive(p_full);
+      l = l * alpha + lt;
+      m = mx;
+#pragma unroll
+      for (int d = 0; d < DV; ++d) O[d] *= alpha;
+      mbar_wait(o_full, j & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < DV / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_o + lane_base + c * 32, v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) O[c * 32 + e] += __uint_as_float(v[e]);
+      }
+      tc_fence_before();
+    }
+    if (qi < a.S) {
+      const float inv = l > 0.f ? 1.f / l : 0.f;
+      bf16* orow = a.out + ((size_t)n * a.S + qi) * a.ld_o + h * DV;
+#pragma unroll
+      for (int d = 0; d < DV; d += 8) {
+        *reinterpret_cast<uint4*>(orow + d) =
+            make_uint4(pack_bf16x2(O[d] * inv, O[d + 1] * inv), pack_bf16x2(O[d + 2] * inv, O[d + 3] * inv),
+                       pack_bf16x2(O[d + 4] * inv, O[d + 5] * inv), pack_bf16x2(O[d + 6] * inv, O[d + 7] * inv));
+      }
+      a.lse[((size_t)n * a.H + h) * a.S + qi] = l > 0.f ? m * a.scale + __logf(l) : 0.f;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc<TMEM_COLS>(tmem);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Backward
+// ------------------------------------------------------------------------------------------------
+template <int DV>
+__global__ void __launch_bounds__(192, 1)
+attn_bwd_tc_kernel(const __grid_constant__ AttnTmaps tm, const AttnArgs a, const int T) {
+  constexpr int V_BYTES = DV * 256;
+  constexpr int TMEM_COLS = 512;
+  constexpr int COL_S = 0, COL_DP = 128, COL_DV = 256, COL_DK = 384, COL_DQ = 448;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sK = smem;
+  uint8_t* sV = sK + ATOM_BYTES;
+  uint8_t* sQ = sV + V_BYTES;            // 2 stages
+  uint8_t* sdO = sQ + 2 * ATOM_BYTES;    // 2 stages
+  uint8_t* sP = sdO + 2 * V_BYTES;       // 2 atoms
+  uint8_t* sdS = sP + 2 * ATOM_BYTES;    // 2 atoms
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sdS + 2 * ATOM_BYTES);
+  uint64_t* kv_full = bars;
+  uint64_t* qdo_full = bars + 1;   // [2]
+  uint64_t* qdo_empty = bars + 3;  // [2]
+  uint64_t* s_full = bars + 5;     // S and dP complete
+  uint64_t* pds_full = bars + 6;   // P and dS written to smem
+  uint64_t* dq_full = bars + 7;    // dQ (and everything before it) complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nh = blockIdx.x % (a.N * a.H);
+  const int j = blockIdx.x / (a.N * a.H);  // key tile; small j = most query tiles = scheduled first
+  const int n = nh / a.H, h = nh % a.H;
+  const int niter = T - j;
+
+  if (threadIdx.x == 0) {
+    if (smem_u32(smem) & 1023u) { printf("pg attention: shared memory base not 1024B aligned\n"); __trap(); }
+    mbar_init(kv_full, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&qdo_full[s], 1); mbar_init(&qdo_empty[s], 1); }
+    mbar_init(s_full, 1);
+    mbar_init(pds_full, 128);
+    mbar_init(dq_full, 1);
+    fence_barrier_init();
+    fence_proxy_async_smem();
+  }
+  if (warp == 5) tmem_alloc<TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(kv_full, ATOM_BYTES + V_BYTES);
+      tma_load_3d(sK, &tm.k, kv_full, h * 64, j * AT, n);
+#pragma unroll
+      for (int v = 0; v < DV / 64; ++v) tma_load_3d(sV + v * ATOM_BYTES, &tm.v, kv_full, h * DV + v * 64, j * AT, n);
+      for (int it = 0; it < niter; ++it) {
+        const int st = it & 1, i = j + it;
+        mbar_wait(&qdo_empty[st], ((it >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&qdo_full[st], ATOM_BYTES + V_BYTES);
+        tma_load_3d(sQ + st * ATOM_BYTES, &tm.q, &qdo_full[st], h * 64, i * AT, n);
+#pragma unroll
+        for (int v = 0; v < DV / 64; ++v)
+          tma_load_3d(sdO + st * V_BYTES + v * ATOM_BYTES, &tm.d_o, &qdo_full[st], h * DV + v * 64, i * AT, n);
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);   // S = Q K^T, dP = dO V^T
+      constexpr uint32_t idesc_dv = umma_idesc_bf16(128, DV, 1, 1);   // dV += P^T dO
+      constexpr uint32_t idesc_dk = umma_idesc_bf16(128, 64, 1, 1);   // dK += dS^T Q
+      constexpr uint32_t idesc_dq = umma_idesc_bf16(128, 64, 0, 1);   // dQ  = dS K
+      const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV), p_addr = smem_u32(sP), ds_addr = smem_u32(sdS);
+      auto issue_s_dp = [&](int st) {
+        const uint32_t q_addr = smem_u32(sQ + st * ATOM_BYTES), do_addr = smem_u32(sdO + st * V_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          umma_bf16_ss(tmem + COL_S, desc_kmajor(q_addr, kk), desc_kmajor(k_addr, kk), idesc_s, kk > 0);
+#pragma unroll
+        for (int kk = 0; kk < DV / 16; ++kk)
+          umma_bf16_ss(tmem + COL_DP, desc_kmajor(do_addr, kk), desc_kmajor(v_addr, kk), idesc_s, kk > 0);
+        umma_commit(s_full);
+      };
+      mbar_wait(kv_full, 0);
+      mbar_wait(&qdo_full[0], 0);
+      tc_fence_after();
+      issue_s_dp(0);
+      for (int it = 0; it < niter; ++it) {
+        const int st = it & 1;
+        const uint32_t q_addr = smem_u32(sQ + st * ATOM_BYTES), do_addr = smem_u32(sdO + st * V_BYTES);
+        mbar_wait(pds_full, it & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)  // K = 128 queries
+          umma_bf16_ss(tmem + COL_DV, desc_mnmajor(p_addr, kk), desc_mnmajor(do_addr, kk), idesc_dv, (it > 0 || kk > 0));
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)
+          umma_bf16_ss(tmem + COL_DK, desc_mnmajor(ds_addr, kk), desc_mnmajor(q_addr, kk), idesc_dk, (it > 0 || kk > 0));
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)  // K = 128 keys
+          umma_bf16_ss(tmem + COL_DQ, desc_kmajor(ds_addr, kk), desc_mnmajor(k_addr, kk), idesc_dq, kk > 0);
+        umma_commit(dq_full);
+        umma_commit(&qdo_empty[st]);
+        if (it + 1 < niter) {
+          mbar_wait(&qdo_full[st ^ 1], ((it + 1) >> 1) & 1);
+          tc_fence_after();
+          issue_s_dp(st ^ 1);
+        }
+      }
+    }
+  } else {
+    // ===================== thread == query row =====================
+    const int r = warp * 32 + lane;
+    const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+    const float sl2 = a.scale * 1.4426950408889634f;
+    const int k0 = j * AT;
+    for (int it = 0; it < niter; ++it) {
+      const int i = j + it;
+      const int qi = i * AT + r;
+      const bool row_ok = qi < a.S;
+      const size_t stat = ((size_t)n * a.H + h) * a.S + qi;
+      const float lse2 = row_ok ? a.lse_in[stat] * 1.4426950408889634f : 0.f;
+      const float delta = row_ok ? a.delta[stat] : 0.f;
+      const int qlim = row_ok ? qi - a.strict : -1;  // invalid rows see no keys
+      const bool need_mask = (it == 0) || (i == T - 1);
+      mbar_wait(s_full, it & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t sv[32], dv[32];
+        tmem_ld_32x32b_x32(tmem + COL_S + lane_base + c * 32, sv);
+        tmem_ld_32x32b_x32(tmem + COL_DP + lane_base + c * 32, dv);
+        tmem_wait_ld();
+        uint32_t pw[16], dw[16];
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) {
+          float p0 = fast_exp2(fmaf(__uint_as_float(sv[e]), sl2, -lse2));
+          float p1 = fast_exp2(fmaf(__uint_as_float(sv[e + 1]), sl2, -lse2));
+          if (need_mask) {
+            if (k0 + c * 32 + e > qlim) p0 = 0.f;
+            if (k0 + c * 32 + e + 1 > qlim) p1 = 0.f;
+          }
+          const float d0 = p0 * (__uint_as_float(dv[e]) - delta);
+          const float d1 = p1 * (__uint_as_float(dv[e + 1]) - delta);
+          pw[e >> 1] = pack_bf16x2(p0, p1);
+          dw[e >> 1] = pack_bf16x2(d0, d1);
+        }
+        store_tile_row_chunk(sP, r, c, pw);
+        store_tile_row_chunk(sdS, r, c, dw);
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(pds_full);
+      mbar_wait(dq_full, it & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem + COL_DQ + lane_base + c * 32, v);
+        tmem_wait_ld();
+        if (row_ok) {
+          float* dst = a.dq_accum + ((size_t)n * a.S + qi) * ((size_t)a.H * 64) + h * 64 + c * 32;
+#pragma unroll
+          for (int e = 0; e < 32; e += 4)
+            atomicAdd(reinterpret_cast<float4*>(dst + e),
+                      make_float4(__uint_as_float(v[e]) * a.scale, __uint_as_float(v[e + 1]) * a.scale,
+                                  __uint_as_float(v[e + 2]) * a.scale, __uint_as_float(v[e + 3]) * a.scale));
+        }
+      }
+      tc_fence_before();
+    }
+    // dV_j, dK_j are complete (the last dq_full commit covers all earlier MMAs); thread == key row.
+    // TMEM loads are warp-aligned instructions: every lane executes them, only the stores are predicated.
+    const int kj = k0 + r;
+    const bool key_ok = kj < a.S;
+    bf16* dvrow = a.dv_out + ((size_t)n * a.S + kj) * a.ld_dv + h * DV;
+#pragma unroll
+    for (int c = 0; c < DV / 32; ++c) {
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(tmem + COL_DV + lane_base + c * 32, v);
+      tmem_wait_ld();
+      if (key_ok) {
+#pragma unroll
+        for (int e = 0; e < 32; e += 8)
+          *reinterpret_cast<uint4*>(dvrow + c * 32 + e) =
+              make_uint4(pack_bf16x2(__uint_as_float(v[e]), __uint_as_float(v[e + 1])),
+                         pack_bf16x2(__uint_as_float(v[e + 2]), __uint_as_float(v[e + 3])),
+                         pack_bf16x2(__uint_as_float(v[e + 4]), __uint_as_float(v[e + 5])),
+                         pack_bf16x2(__uint_as_float(v[e + 6]), __uint_as_float(v[e + 7])));
+      }
+    }
+    bf16* dkrow = a.dk_out + ((size_t)n * a.S + kj) * a.ld_dk + h * 64;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(tmem + COL_DK + lane_base + c * 32, v);
+      tmem_wait_ld();
+      if (key_ok) {
+#pragma unroll
+        for (int e = 0; e < 32; e += 8)
+          *reinterpret_cast<uint4*>(dkrow + c * 32 + e) = make_uint4(
+              pack_bf16x2(__uint_as_float(v[e]) * a.scale, __uint_as_float(v[e + 1]) * a.scale),
+              pack_bf16x2(__uint_as_float(v[e + 2]) * a.scale, __uint_as_float(v[e + 3]) * a.scale),
+              pack_bf16x2(__uint_as_float(v[e + 4]) * a.scale, __uint_as_float(v[e + 5]) * a.scale),
+              pack_bf16x2(__uint_as_float(v[e + 6]) * a.scale, __uint_as_float(v[e + 7]) * a.scale));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc<TMEM_COLS>(tmem);
+  }
+}
+
+// fp32 dq accumulator [P, H*64] -> bf16 dq (pitch ld_dq)
+__global__ void attn_dq_convert_kernel(const float* __restrict__ acc, bf16* __restrict__ dq, int64_t ld_dq, long long P,
+                                       int width) {
+  const int groups = width / 8;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < P * groups;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long row = idx / groups;
+    const int c = (int)(idx % groups) * 8;
+    const float4 x0 = *reinterpret_cast<const float4*>(acc + row * width + c);
+    const float4 x1 = *reinterpret_cast<const float4*>(acc + row * width + c + 4);
+    *reinterpret_cast<uint4*>(dq + row * ld_dq + c) =
+        make_uint4(pack_bf16x2(x0.x, x0.y), pack_bf16x2(x0.z, x0.w), pack_bf16x2(x1.x, x1.y), pack_bf16x2(x1.z, x1.w));
+  }
+}
+
+int make_attn_map(CUtensorMap* out, const bf16* base, int64_t ld, int width, int S, int N) {
+  uint64_t dims[3] = {(uint64_t)width, (uint64_t)S, (uint64_t)N};
+  uint64_t strides[2] = {(uint64_t)ld * 2, (uint64_t)S * (uint64_t)ld * 2};
+  uint32_t box[3] = {64, (uint32_t)AT, 1};
+  return pg_make_tmap_nd_bf16(out, base, 3, dims, strides, box, 1);
+}
+
+int attn_check_tc(const AttnArgs& a, const char* who) {
+  PG_REQUIRE(a.dk == 64, "%s: tcgen05 path needs 64-wide q/k head slots (dk=%d)", who, a.dk);
+  PG_REQUIRE(a.dv == 64 || a.dv == 128, "%s: tcgen05 path needs dv in {64,128} (dv=%d)", who, a.dv);
+  return 0;
+}
+
+int attn_fwd_tc(const AttnArgs& a, cudaStream_t stream) {
+  if (attn_check_tc(a, "pg_causal_attn_fwd")) return 1;
+  PG_REQUIRE(a.ld_o % 8 == 0, "pg_causal_attn_fwd: output pitch must be a multiple of 8");
+  AttnTmaps tm;
+  if (make_attn_map(&tm.q, a.q, a.ld_q, a.H * 64, a.S, a.N)) return 1;
+  if (make_attn_map(&tm.k, a.k, a.ld_k, a.H * 64, a.S, a.N)) return 1;
+  if (make_attn_map(&tm.v, a.v, a.ld_v, a.H * a.dv, a.S, a.N)) return 1;
+  tm.d_o = tm.v;
+  const int T = (a.S + AT - 1) / AT;
+  const unsigned grid = (unsigned)(a.N * a.H * T);
+  if (a.dv == 64) {
+    constexpr int SMEM = ATOM_BYTES * (1 + 2 + 2 + 2) + 256;
+    PG_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    attn_fwd_tc_kernel<64><<<grid, 192, SMEM, stream>>>(tm, a, T);
+  } else {
+    constexpr int SMEM = ATOM_BYTES * (1 + 2 + 4 + 2) + 256;
+    PG_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    attn_fwd_tc_kernel<128><<<grid, 192, SMEM, stream>>>(tm, a, T);
+  }
+  return pg_check_launch("pg_causal_attn_fwd(tcgen05)");
+}
+
+int attn_bwd_tc(const AttnArgs& a, cudaStream_t stream) {
+  if (attn_check_tc(a, "pg_causal_attn_bwd")) return 1;
+  PG_REQUIRE(a.dq_accum != nullptr, "pg_causal_attn_bwd: dq_accum scratch is required by the tcgen05 path");
+  PG_REQUIRE(a.ld_dq % 8 == 0 && a.ld_dk % 8 == 0 && a.ld_dv % 8 == 0, "pg_causal_attn_bwd: pitches must be multiples of 8");
+  AttnTmaps tm;
+  if (make_attn_map(&tm.q, a.q, a.ld_q, a.H * 64, a.S, a.N)) return 1;
+  if (make_attn_map(&tm.k, a.k, a.ld_k, a.H * 64, a.S, a.N)) return 1;
+  if (make_attn_map(&tm.v, a.v, a.ld_v, a.H * a.dv, a.S, a.N)) return 1;
+  if (make_attn_map(&tm.d_o, a.d_o, a.ld_do, a.H * a.dv, a.S, a.N)) return 1;
+  const int T = (a.S + AT - 1) / AT;
+  const unsigned grid = (unsigned)(a.N * a.H * T);
+  if (a.dv == 64) {
+    constexpr int SMEM = ATOM_BYTES * (1 + 1 + 2 + 2 + 2 + 2) + 256;
+    PG_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    attn_bwd_tc_kernel<64><<<grid, 192, SMEM, stream>>>(tm, a, T);
+  } else {
+    constexpr int SMEM = ATOM_BYTES * (1 + 2 + 2 + 4 + 2 + 2) + 256;
+    PG_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    attn_bwd_tc_kernel<128><<<grid, 192, SMEM, stream>>>(tm, a, T);
+  }
+  if (pg_check_launch("pg_causal_attn_bwd(tcgen05)")) return 1;
+  const long long P = (long long)a.N * a.S;
+  const int width = a.H * 64;
+  long long blocks = (P * (width / 8) + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  attn_dq_convert_kernel<<<(unsigned)blocks, 256, 0, stream>>>(a.dq_accum, a.dq, a.ld_dq, P, width);
+  return pg_check_launch("pg_causal_attn_bwd(dq convert)");
+}
+
 }  // namespace

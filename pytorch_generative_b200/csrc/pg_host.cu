@@ -1,5 +1,7 @@
 // pg_host.cu — host-side plumbing of the C ABI: error strings, device query, CUtensorMap encoding.
 #include <stdarg.h>
+
+#include <atomic>
 #include <string.h>
 
 #include "../../include/pg_b200.h"
@@ -14,7 +16,10 @@ void pg_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static std::atomic<unsigned long long> g_launches{0};
+
 int pg_check_launch(const char* what) {
+  ++g_launches;  // one call per kernel launch: the count bench.py reports as gpu_launches
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     pg_set_error("%s: launch failed: %s", what, cudaGetErrorString(e));
@@ -38,6 +43,7 @@ int pg_num_sms() {
   return cached[dev];
 }
 extern "C" int pg_sm_count(void) { return pg_num_sms(); }
+extern "C" unsigned long long pg_launch_count(void) { return g_launches.load(); }
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,

@@ -1,0 +1,78 @@
+"""Base classes of the drop-in models (API of reference pytorch_generative/models/base.py:28-120).
+
+Behavioural contract kept from the reference:
+  * `__call__` records the image shape of the first 4-D input in buffers `_c, _h, _w` (int64 scalars that are
+    part of the state dict) — base.py:41-46, 55-61;
+  * `load_state_dict` registers those buffers first when the checkpoint has them — base.py:48-53;
+  * `sample(n_samples=None, conditioned_on=None)` walks the image in raster order, draws all channels of one
+    pixel from `sample_fn(logits[:, :, r, c])` and only overwrites entries < 0 — base.py:97-120;
+  * `device` property — base.py:63-65.
+"""
+
+import abc
+
+import torch
+from torch import nn
+
+
+def _bernoulli_from_logits(logits):
+    """Default `sample_fn` (reference base.py:9-10): one Bernoulli draw per logit."""
+    return torch.bernoulli(torch.sigmoid(logits))
+
+
+class GenerativeModel(abc.ABC, nn.Module):
+    """Shape-tracking nn.Module base."""
+
+    def __call__(self, x, *args, **kwargs):
+        if getattr(self, "_c", None) is None and x.dim() == 4:
+            self._register_shape(*x.shape[1:])
+        return super().__call__(x, *args, **kwargs)
+
+    def load_state_dict(self, state_dict, strict=True):
+        if "_c" in state_dict and not getattr(self, "_c", None):
+            self._register_shape(state_dict["_c"], state_dict["_h"], state_dict["_w"])
+        return super().load_state_dict(state_dict, strict)
+
+    def _register_shape(self, c, h, w):
+        as_t = lambda v: v if torch.is_tensor(v) else torch.tensor(v)
+        self.register_buffer("_c", as_t(c))
+        self.register_buffer("_h", as_t(h))
+        self.register_buffer("_w", as_t(w))
+
+    @property
+    def device(self):
+        return next(self.parameters()).device
+
+    @abc.abstractmethod
+    def sample(self, n_samples):
+        ...
+
+
+class AutoregressiveModel(GenerativeModel):
+    """Adds raster-scan ancestral sampling on top of `forward`."""
+
+    def __init__(self, sample_fn=None):
+        super().__init__()
+        self._sample_fn = sample_fn or _bernoulli_from_logits
+
+    def _start_canvas(self, n_samples, conditioned_on):
+        assert (
+            n_samples is not None or conditioned_on is not None
+        ), 'Must provided one, and only one, of "n_samples" or "conditioned_on"'
+        if conditioned_on is not None:
+            return conditioned_on.clone()
+        shape = (n_samples, int(self._c), int(self._h), int(self._w))
+        return torch.full(shape, -1.0, device=self.device)
+
+    @torch.no_grad()
+    def sample(self, n_samples=None, conditioned_on=None):
+        """Generates samples pixel by pixel; entries of `conditioned_on` that are >= 0 are kept."""
+        canvas = self._start_canvas(n_samples, conditioned_on)
+        n, c, h, w = canvas.shape
+        for row in range(h):
+            for col in range(w):
+                logits = self.forward(canvas)[:, :, row, col]
+                drawn = self._sample_fn(logits).view(n, c)
+                current = canvas[:, :, row, col]
+                canvas[:, :, row, col] = torch.where(current < 0, drawn, current)
+        return canvas

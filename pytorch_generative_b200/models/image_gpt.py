@@ -1,0 +1,215 @@
+"""ImageGPT on the B200 path — API of reference models/autoregressive/image_gpt.py:21-109.
+
+Module tree, parameter names and shapes are the reference's (`_pos`, `_input`, `_transformer.{i}.{_ln1,_ln2,
+_attn.{_q,_kv,_proj},_out.{0,2}}`, `_ln`, `_out`), so checkpoints are interchangeable.  `forward` does not walk
+that tree: the whole stack runs as ONE autograd node over pixel-major tensors —
+
+    stream x (fp32 [P, C])  --LN-->  bf16  --GEMM(q|k|v)-->  causal attention  --GEMM(proj)+x--> h (fp32)
+    h --LN--> bf16 --GEMM(4C)+GELU--> bf16 --GEMM(C) + x + h--> next stream      (x <- x + h + mlp, the
+                                                                                  reference's double residual)
+
+with every bias / activation / residual folded into a GEMM epilogue, the residual stream and all summed
+gradients kept in fp32, and bf16 used only for tensor-core operands.
+"""
+
+import torch
+from torch import nn
+
+from .. import _lib as L
+from .. import nn as pg_nn
+from .. import ops
+from ..nn.modules import pack_qkv_weights
+from . import base
+
+F32, BF16 = torch.float32, torch.bfloat16
+PARAMS_PER_BLOCK = 14
+
+
+class TransformerBlock(nn.Module):
+    """Holds the parameters of one block (reference image_gpt.py:21-52); standalone `forward` composes the
+    drop-in nn modules, the fused model path reads the parameters directly."""
+
+    def __init__(self, n_channels, n_attention_heads):
+        super().__init__()
+        self._ln1 = pg_nn.NCHWLayerNorm(n_channels)
+        self._ln2 = pg_nn.NCHWLayerNorm(n_channels)
+        self._attn = pg_nn.CausalAttention(in_channels=n_channels, n_heads=n_attention_heads,
+                                           embed_channels=n_channels, out_channels=n_channels)
+        self._out = nn.Sequential(
+            nn.Conv2d(in_channels=n_channels, out_channels=4 * n_channels, kernel_size=1),
+            nn.GELU(),
+            nn.Conv2d(in_channels=4 * n_channels, out_channels=n_channels, kernel_size=1),
+        )
+
+    def flat_params(self):
+        a = self._attn
+        return [self._ln1.weight, self._ln1.bias, a._q.weight, a._q.bias, a._kv.weight, a._kv.bias, a._proj.weight,
+                a._proj.bias, self._ln2.weight, self._ln2.bias, self._out[0].weight, self._out[0].bias,
+                self._out[2].weight, self._out[2].bias]
+
+
+class _ImageGPTStack(torch.autograd.Function):
+    """forward(x_nchw, params...) -> logits_nchw; one node for the whole network."""
+
+    @staticmethod
+    def forward(ctx, x, n_heads, eps, *params):
+        pos, in_w, in_b = params[0], params[1], params[2]
+        n_blocks = (len(params) - 7) // PARAMS_PER_BLOCK
+        ln_w, ln_b, out_w, out_b = params[-4:]
+        n, cin, h, w = x.shape
+        S, P, H = h * w, n * h * w, n_heads
+        C = in_w.shape[0]
+        keep = any(ctx.needs_input_grad)
+
+        x_in = (x + pos).contiguous()
+        xs = torch.empty(P, C, dtype=F32, device=x.device)
+        L.conv_small_fwd(x_in, in_w.detach().contiguous(), in_b.detach(), (in_w.shape[2] // 2, in_w.shape[3] // 2),
+                         out_f32=xs)
+        saved = []
+        for b in range(n_blocks):
+            (ln1_w, ln1_b, q_w, q_b, kv_w, kv_b, p_w, p_b, ln2_w, ln2_b, f1_w, f1_b, f2_w,
+             f2_b) = params[3 + b * PARAMS_PER_BLOCK: 3 + (b + 1) * PARAMS_PER_BLOCK]
+            wq, bq, wkv, bkv, meta = pack_qkv_weights(q_w, q_b, kv_w, kv_b, H, C, C, C, C)
+            wqkv = torch.cat((wq, wkv))
+            bqkv = torch.cat((bq, bkv))
+            dv_slot, slot = meta["dv_slot"], ops.HEAD_SLOT
+            a1, _, mean1, rstd1 = ops.layernorm_fwd(xs, ln1_w.detach(), ln1_b.detach(), eps)
+            qkv, _, _ = ops.linear_fwd(a1, wqkv, bqkv)
+            q, k, v = qkv[:, : H * slot], qkv[:, H * slot: 2 * H * slot], qkv[:, 2 * H * slot:]
+            o, lse = ops.attn_fwd(q, k, v, n, S, H, meta["dk"], dv_slot, False)
+            cols_v = meta["rows_v"] - H * slot
+            if meta["dv"] == dv_slot:
+                wp = ops.pack_weight(p_w)
+            else:
+                wp32 = torch.zeros(C, H * dv_slot, dtype=F32, device=x.device)
+                wp32[:, cols_v] = p_w.detach().reshape(C, -1)
+                wp = ops.to_bf16(wp32)
+            _, _, hres = ops.linear_fwd(o, wp, p_b.detach(), res0=xs, want_bf16=False, want_f32=True)
+            a2, _, mean2, rstd2 = ops.layernorm_fwd(hres, ln2_w.detach(), ln2_b.detach(), eps)
+            w1, w2 = ops.pack_weight(f1_w), ops.pack_weight(f2_w)
+            g, u, _ = ops.linear_fwd(a2, w1, f1_b.detach(), act=L.ACT_GELU, want_pre=True)
+            _, _, xs_new = ops.linear_fwd(g, w2, f2_b.detach(), res0=xs, res1=hres, want_bf16=False, want_f32=True)
+            if keep:
+                saved.append(dict(xs=xs, a1=a1, qkv=qkv, o=o, lse=lse, h=hres, a2=a2, u=u, g=g, mean1=mean1, rstd1=rstd1,
+                                  mean2=mean2, rstd2=rstd2, wqkv=wqkv, wp=wp, w1=w1, w2=w2, meta=meta, cols_v=cols_v))
+            xs = xs_new
+        af, _, mean_f, rstd_f = ops.layernorm_fwd(xs, ln_w.detach(), ln_b.detach(), eps)
+        cout = out_w.shape[0]
+        wo = ops.pack_weight(out_w)
+        _, _, logits_pm = ops.linear_fwd(af, wo, out_b.detach(), want_bf16=False, want_f32=True)
+        if keep:
+            ctx.saved = dict(blocks=saved, x_in=x_in, xs_final=xs, af=af, mean_f=mean_f, rstd_f=rstd_f, wo=wo,
+                             params=params, dims=(n, cin, h, w, C, H, cout), eps=eps)
+        return ops.pm_to_nchw(logits_pm, n, cout, h, w)
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        sv = ctx.saved
+        params = sv["params"]
+        n, cin, h, w, C, H, cout = sv["dims"]
+        S, P = h * w, n * h * w
+        dev = dlogits.device
+        slot = ops.HEAD_SLOT
+        n_blocks = len(sv["blocks"])
+        grads = [None] * len(params)
+        ln_w = params[-4]
+
+        # head: logits = 1x1(LN(x))
+        dl = ops.nchw_to_pm(dlogits, BF16, width=ops.round_up(cout, 8))
+        grads[-1] = ops.bias_grad(dl[:, :cout])
+        dwo = torch.zeros(ops.round_up(cout, 8), C, dtype=F32, device=dev)
+        ops.linear_wgrad(dl, sv["af"], dwo)
+        grads[-2] = dwo[:cout].reshape(cout, C, 1, 1)
+        daf = ops.linear_dgrad(dl[:, :cout], sv["wo"])
+        dx, dx_b, grads[-4], grads[-3] = ops.layernorm_bwd(daf, sv["xs_final"], ln_w.detach(), sv["mean_f"], sv["rstd_f"])
+        del daf
+
+        for b in reversed(range(n_blocks)):
+            blk = sv["blocks"][b]
+            base_i = 3 + b * PARAMS_PER_BLOCK
+            (ln1_w, _, q_w, _, kv_w, _, p_w, _, ln2_w, _, f1_w, _, f2_w, _) = params[base_i: base_i + PARAMS_PER_BLOCK]
+            meta, dv_slot = blk["meta"], blk["meta"]["dv_slot"]
+            # x_new = x + h + fc2(gelu(fc1(ln2(h))))
+            grads[base_i + 13] = ops.bias_grad(dx)
+            dw2 = torch.zeros(C, 4 * C, dtype=F32, device=dev)
+            ops.linear_wgrad(dx_b, blk["g"], dw2)
+            grads[base_i + 12] = dw2.view(C, 4 * C, 1, 1)
+            du = ops.linear_dgrad(dx_b, blk["w2"], aux=blk["u"], dact=L.ACT_GELU)
+            grads[base_i + 11] = ops.bias_grad(du)
+            dw1 = torch.zeros(4 * C, C, dtype=F32, device=dev)
+            ops.linear_wgrad(du, blk["a2"], dw1)
+            grads[base_i + 10] = dw1.view(4 * C, C, 1, 1)
+            da2 = ops.linear_dgrad(du, blk["w1"])
+            del du
+            # h receives: LN2 path + direct (x_new = ... + h)
+            dh, dh_b, grads[base_i + 8], grads[base_i + 9] = ops.layernorm_bwd(
+                da2, blk["h"], ln2_w.detach(), blk["mean2"], blk["rstd2"], dres0=dx)
+            del da2
+            # h = x + proj(attn)
+            grads[base_i + 7] = ops.bias_grad(dh)
+            dwp = torch.zeros(C, H * dv_slot, dtype=F32, device=dev)
+            ops.linear_wgrad(dh_b, blk["o"], dwp)
+            grads[base_i + 6] = (dwp if meta["dv"] == dv_slot else dwp[:, blk["cols_v"]]).reshape(C, C, 1, 1)
+            do = ops.linear_dgrad(dh_b, blk["wp"])
+            qkv = blk["qkv"]
+            q, k, v = qkv[:, : H * slot], qkv[:, H * slot: 2 * H * slot], qkv[:, 2 * H * slot:]
+            dqkv = torch.empty_like(qkv)
+            ops.attn_bwd(q, k, v, blk["o"], do, blk["lse"], dqkv[:, : H * slot], dqkv[:, H * slot: 2 * H * slot],
+                         dqkv[:, 2 * H * slot:], n, S, H, meta["dk"], dv_slot, False)
+            del do
+            dbqkv = ops.bias_grad(dqkv)
+            dwqkv = torch.zeros(blk["wqkv"].shape, dtype=F32, device=dev)
+            ops.linear_wgrad(dqkv, blk["a1"], dwqkv)
+            rq, rv = meta["rows_q"], meta["rows_v"]
+            grads[base_i + 2] = dwqkv[rq].reshape(C, C, 1, 1)
+            grads[base_i + 3] = dbqkv[rq]
+            grads[base_i + 4] = torch.cat((dwqkv[rq + H * slot], dwqkv[rv + H * slot])).reshape(2 * C, C, 1, 1)
+            grads[base_i + 5] = torch.cat((dbqkv[rq + H * slot], dbqkv[rv + H * slot]))
+            da1 = ops.linear_dgrad(dqkv, blk["wqkv"])
+            del dqkv
+            # x receives: LN1 path + direct from h (dh) + direct from x_new (dx)
+            dx, dx_b, grads[base_i + 0], grads[base_i + 1] = ops.layernorm_bwd(
+                da1, blk["xs"], ln1_w.detach(), blk["mean1"], blk["rstd1"], dres0=dx, dres1=dh)
+            del da1, dh, dh_b
+            sv["blocks"][b] = None  # release this block's activations
+
+        in_w = params[1]
+        dw_in = torch.zeros_like(in_w)
+        db_in = torch.zeros(C, dtype=F32, device=dev)
+        dx_in = torch.empty(n, cin, h, w, dtype=F32, device=dev)
+        L.conv_small_bwd(sv["x_in"], in_w.detach().contiguous(), dx, (in_w.shape[2] // 2, in_w.shape[3] // 2), dw=dw_in,
+                         dbias=db_in, dx=dx_in)
+        grads[1], grads[2] = dw_in, db_in
+        grads[0] = dx_in.sum(dim=0, keepdim=True)
+        ctx.saved = None
+        return (dx_in if ctx.needs_input_grad[0] else None, None, None, *grads)
+
+
+class ImageGPT(base.AutoregressiveModel):
+    """The (convolutional) ImageGPT model — constructor of reference image_gpt.py:64-103."""
+
+    def __init__(self, in_channels=1, out_channels=1, in_size=28, n_transformer_blocks=8, n_attention_heads=4,
+                 n_embedding_channels=16, sample_fn=None):
+        super().__init__(sample_fn)
+        self._pos = nn.Parameter(torch.zeros(1, in_channels, in_size, in_size))
+        self._input = pg_nn.CausalConv2d(mask_center=True, in_channels=in_channels,
+                                         out_channels=n_embedding_channels, kernel_size=3, padding=1)
+        self._transformer = nn.ModuleList(
+            TransformerBlock(n_channels=n_embedding_channels, n_attention_heads=n_attention_heads)
+            for _ in range(n_transformer_blocks)
+        )
+        self._ln = pg_nn.NCHWLayerNorm(n_embedding_channels)
+        self._out = nn.Conv2d(in_channels=n_embedding_channels, out_channels=out_channels, kernel_size=1)
+        self._n_heads = n_attention_heads
+        if n_embedding_channels % 8 != 0:
+            raise NotImplementedError("ImageGPT: n_embedding_channels must be a multiple of 8 on the B200 path")
+
+    def forward(self, x):
+        if not x.is_cuda:
+            raise RuntimeError("ImageGPT (B200 path) needs CUDA tensors; there is no CPU fallback")
+        self._input.weight.data *= self._input.mask  # same in-place side effect as the reference's CausalConv2d
+        flat = [self._pos, self._input.weight, self._input.bias]
+        for blk in self._transformer:
+            flat.extend(blk.flat_params())
+        flat.extend([self._ln.weight, self._ln.bias, self._out.weight, self._out.bias])
+        return _ImageGPTStack.apply(x.float(), self._n_heads, self._ln.eps, *flat)

@@ -354,7 +354,8 @@ def test_attention_fwd_bwd(L, case, impl):
     dqkv = torch.full((P, H * (2 * dk + dv)), float("nan"), device=_dev(), dtype=torch.bfloat16)
     dq, dk_, dv_ = dqkv[:, : H * dk], dqkv[:, H * dk: 2 * H * dk], dqkv[:, 2 * H * dk:]
     delta = torch.empty(N, H, S, device=_dev())
-    L.causal_attn_bwd(q, k, v, o, do, lse, delta, dq, dk_, dv_, N, S, H, dk, dv, strict, impl=impl)
+    dq_acc = torch.zeros(P, H * dk, device=_dev())
+    L.causal_attn_bwd(q, k, v, o, do, lse, delta, dq_acc, dq, dk_, dv_, N, S, H, dk, dv, strict, impl=impl)
     torch.cuda.synchronize()
     assert_close("attn dq", dq, dq_ref, rtol=2 ** -6, atol=2e-3)
     assert_close("attn dk", dk_, dk_ref, rtol=2 ** -6, atol=2e-3)
