@@ -334,6 +334,18 @@ def _attn_inputs(N, S, H, dk, dv, seed=12):
     return q, k, v, do
 
 
+def _to_slots(t, H, d, slot):
+    """[P, H*d] -> [P, H*slot] with each head in a zero-padded slot (layout of the tcgen05 kernels)."""
+    P = t.shape[0]
+    out = torch.zeros(P, H, slot, device=t.device, dtype=t.dtype)
+    out[:, :, :d] = t.reshape(P, H, d)
+    return out.reshape(P, H * slot)
+
+
+def _from_slots(t, H, d, slot):
+    return t.reshape(t.shape[0], H, slot)[:, :, :d].reshape(t.shape[0], H * d)
+
+
 @pytest.mark.parametrize("impl", [1, 0])
 @pytest.mark.parametrize("case", ATTN_CASES)
 def test_attention_fwd_bwd(L, case, impl):
@@ -341,25 +353,33 @@ def test_attention_fwd_bwd(L, case, impl):
     q, k, v, do = _attn_inputs(N, S, H, dk, dv)
     P = N * S
     o_ref, lse_ref, dq_ref, dk_ref, dv_ref = _attn_ref(q, k, v, do, N, S, H, dk, dv, strict)
-    o = torch.full((P, H * dv), float("nan"), device=_dev(), dtype=torch.bfloat16)
+    if impl == 0:  # tensor-core kernels: 64-wide q/k slots, 64/128-wide v slots, scale from the true dk
+        ks, vs = 64, (64 if dv <= 64 else 128)
+        q, k, v, do = _to_slots(q, H, dk, ks), _to_slots(k, H, dk, ks), _to_slots(v, H, dv, vs), _to_slots(do, H, dv, vs)
+    else:
+        ks, vs = dk, dv
+    o = torch.full((P, H * vs), float("nan"), device=_dev(), dtype=torch.bfloat16)
     lse = torch.empty(N, H, S, device=_dev())
-    L.causal_attn_fwd(q, k, v, o, lse, N, S, H, dk, dv, strict, impl=impl)
+    L.causal_attn_fwd(q, k, v, o, lse, N, S, H, ks, vs, strict, impl=impl, dk_true=dk)
     torch.cuda.synchronize()
-    assert_close("attn o", o, o_ref, rtol=2 ** -7, atol=1e-3)
+    assert_close("attn o", _from_slots(o, H, dv, vs), o_ref, rtol=2 ** -7, atol=1e-3)
     if strict:
         assert (o.view(N, S, -1)[:, 0] == 0).all(), "strict mask: first position must be exactly zero"
         assert_close("attn lse", lse[:, :, 1:], lse_ref[:, :, 1:], rtol=1e-3, atol=1e-3)
     else:
         assert_close("attn lse", lse, lse_ref, rtol=1e-3, atol=1e-3)
-    dqkv = torch.full((P, H * (2 * dk + dv)), float("nan"), device=_dev(), dtype=torch.bfloat16)
-    dq, dk_, dv_ = dqkv[:, : H * dk], dqkv[:, H * dk: 2 * H * dk], dqkv[:, 2 * H * dk:]
+    dq = torch.full((P, H * ks), float("nan"), device=_dev(), dtype=torch.bfloat16)
+    dk_ = torch.full((P, H * ks), float("nan"), device=_dev(), dtype=torch.bfloat16)
+    dv_ = torch.full((P, H * vs), float("nan"), device=_dev(), dtype=torch.bfloat16)
     delta = torch.empty(N, H, S, device=_dev())
-    dq_acc = torch.zeros(P, H * dk, device=_dev())
-    L.causal_attn_bwd(q, k, v, o, do, lse, delta, dq_acc, dq, dk_, dv_, N, S, H, dk, dv, strict, impl=impl)
+    dq_acc = torch.zeros(P, H * ks, device=_dev())
+    L.causal_attn_bwd(q, k, v, o, do, lse, delta, dq_acc, dq, dk_, dv_, N, S, H, ks, vs, strict, impl=impl, dk_true=dk)
     torch.cuda.synchronize()
-    assert_close("attn dq", dq, dq_ref, rtol=2 ** -6, atol=2e-3)
-    assert_close("attn dk", dk_, dk_ref, rtol=2 ** -6, atol=2e-3)
-    assert_close("attn dv", dv_, dv_ref, rtol=2 ** -6, atol=2e-3)
+    assert_close("attn dq", _from_slots(dq, H, dk, ks), dq_ref, rtol=2 ** -6, atol=2e-3)
+    assert_close("attn dk", _from_slots(dk_, H, dk, ks), dk_ref, rtol=2 ** -6, atol=2e-3)
+    assert_close("attn dv", _from_slots(dv_, H, dv, vs), dv_ref, rtol=2 ** -6, atol=2e-3)
+    if impl == 0 and dk < ks:
+        assert (dq.reshape(P, H, ks)[:, :, dk:] == 0).all() and (dk_.reshape(P, H, ks)[:, :, dk:] == 0).all()
 
 
 # --------------------------------------------------------------------------------------------------
