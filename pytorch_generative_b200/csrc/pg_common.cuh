@@ -47,6 +47,10 @@ int pg_make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint
 int pg_make_tmap_nd_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                          const uint64_t* strides_bytes /* rank-1 entries */, const uint32_t* box,
                          int swizzle128);
+int pg_make_tmap_nd(CUtensorMap* out, const void* base, int elem_bytes, int rank, const uint64_t* dims,
+                    const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes);
+int pg_make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t rows, uint64_t cols, uint64_t ld,
+                    uint32_t box_rows, uint32_t box_cols, int swizzle_bytes);
 int pg_num_sms();
 
 // ----------------------------------------------------------------------------------------------
@@ -263,10 +267,30 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
 
 // Activation ids (PG_ACT_*) come from include/pg_b200.h.
 
+__device__ __forceinline__ float pg_tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float pg_exp2_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// atanh(erf(x / sqrt 2)) ~= x (c0 + c1 x^2 + c2 x^4): least-squares fit on [-8, 8] (tools: see DESIGN.md)
+__device__ __forceinline__ float pg_gelu_q(float x) {
+  x = fminf(fmaxf(x, -8.f), 8.f);  // the fit is monotone on [-8, 8]; tanh is saturated there (q(8) = 13.7)
+  const float x2 = x * x;
+  return x * fmaf(x2, fmaf(x2, -0.0003563930330798993f, 0.037032072878891306f), 0.7974856909542073f);
+}
+
 __device__ __forceinline__ float pg_act_fwd(int act, float x) {
   switch (act) {
     case PG_ACT_RELU: return fmaxf(x, 0.f);
-    case PG_ACT_GELU: return 0.5f * x * (1.f + erff(x * 0.70710678118654752f));
+    case PG_ACT_GELU: {  // erf-GELU through Phi(x) = 0.5 (1 + tanh(q(x))), q fitted: |gelu err| < 3e-5
+      const float hx = 0.5f * x;
+      return fmaf(hx, pg_tanh_fast(pg_gelu_q(x)), hx);
+    }
     case PG_ACT_ELU: return x > 0.f ? x : expm1f(x);
     case PG_ACT_TANH: return tanhf(x);
     default: return x;
@@ -276,8 +300,11 @@ __device__ __forceinline__ float pg_act_fwd(int act, float x) {
 __device__ __forceinline__ float pg_act_bwd(int act, float x) {
   switch (act) {
     case PG_ACT_RELU: return x > 0.f ? 1.f : 0.f;
-    case PG_ACT_GELU:
-      return 0.5f * (1.f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
+    case PG_ACT_GELU: {  // Phi(x) + x phi(x)
+      const float phi_cdf = fmaf(0.5f, pg_tanh_fast(pg_gelu_q(x)), 0.5f);
+      const float e = pg_exp2_fast(x * x * -0.72134752044448170f);
+      return fmaf(x * 0.3989422804014327f, e, phi_cdf);
+    }
     case PG_ACT_ELU: return x > 0.f ? 1.f : __expf(x);
     case PG_ACT_TANH: {
       float t = tanhf(x);

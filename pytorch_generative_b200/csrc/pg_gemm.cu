@@ -3,14 +3,20 @@
 // One persistent CTA per SM, warp-specialised:
 //   warp 0 (one lane)  TMA producer: global -> 128B-swizzled shared-memory stages, mbarrier expect_tx
 //   warp 1 (one lane)  MMA issuer:   tcgen05.mma cta_group::1, M=128, N=BN, K=16 per instruction,
-//                                    accumulator in TMEM (double buffered when 2*BN <= 512 columns)
+//                                    accumulator in TMEM, double buffered (2*BN <= 512 columns)
 //   warp 2             TMEM allocator / deallocator
-//   warps 4..7         epilogue: tcgen05.ld (lane == output row) -> fused bias / act' / residual /
-//                                activation -> global stores (bf16 and/or fp32, or fp32 atomics for split-K)
-// Operand majors are template parameters so that forward (K,K), dgrad (K,MN) and wgrad (MN,MN) all read
-// the tensors where they lie: no transposed copies of activations or weights are ever materialised.
+//   warps 4..7         epilogue: tcgen05.ld (lane == output row), fused bias / act' / residual / activation.
+// Epilogue I/O is staged through shared memory so that HBM only ever sees full lines: the fp32 residual
+// tiles and the bf16 pre-activation tile arrive by TMA load (prefetched two 32-column chunks ahead), results
+// leave by TMA store from swizzled slabs (double buffered, so chunk c+1 is computed while chunk c drains).
+// Shapes TMA cannot express (pitch not 16-byte aligned, fp32-atomic accumulation for split-K wgrad) take the
+// direct register->global path.
+// Operand majors are template parameters so that forward (K,K), dgrad (K,MN) and wgrad (MN,MN) all read the
+// tensors where they lie: no transposed copies of activations or weights are ever materialised.
 //
 // Replaces: every 1x1 nn.Conv2d forward/backward on the reference path (see include/pg_b200.h).
+#include <string.h>
+
 #include "../../include/pg_b200.h"
 #include "pg_common.cuh"
 
@@ -19,6 +25,13 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle span
 constexpr int A_STAGE_BYTES = BM * BK * 2;
+constexpr int SLAB_F32 = BM * 128;  // [128 rows][32 fp32], 128B swizzle
+constexpr int SLAB_BF16 = BM * 64;  // [128 rows][32 bf16], 64B swizzle
+constexpr int SMEM_LIMIT = 232448;  // 227 KB
+
+struct EpiMaps {
+  CUtensorMap res0, res1, aux, out_f32, out_bf16, out_pre;
+};
 
 struct GemmParams {
   int M, N, K;
@@ -26,13 +39,18 @@ struct GemmParams {
   int k_iters;      // ceil(K / BK)
   int k_per_split;  // k iterations per split
   int splits;
-  int vec_ok;       // all epilogue pointers/pitches allow 16-byte vector access
+  int stages;       // smem pipeline depth
+  int vec_ok;       // all epilogue pointers/pitches allow 16-byte vector access (direct path)
+  // staged (TMA) epilogue plan
+  int staged;
+  int epi_stage_bytes;
+  int off_res0, off_res1, off_aux, off_outf, off_outb, off_outp;  // slab offsets inside an epilogue stage, -1 = absent
+  int in_bytes;  // bytes TMA-loaded per chunk (res0 + res1 + aux slabs)
   pg_gemm_epilogue epi;
 };
 
 // ------------------------------------------------------------------------------------------------
-// Epilogue on one row segment: `vals` are 32 consecutive fp32 accumulator columns of output row `row`
-// starting at column `col0`; `ncols` (<= 32) of them are inside the matrix.
+// Direct epilogue (generic fallback): `acc` = 32 consecutive fp32 accumulator columns of output row `row`.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void epilogue_row32(const GemmParams& p, int row, int col0, int ncols, bool first_split,
                                                const uint32_t (&acc)[32]) {
@@ -73,28 +91,20 @@ __device__ __forceinline__ void epilogue_row32(const GemmParams& p, int row, int
       for (int i = 0; i < ncols; ++i) v[i] *= pg_act_bwd(e.dact, __bfloat162float(aux[i]));
     }
   }
-  if (first_split && e.res0) {
-    const float* r = e.res0 + (size_t)row * e.ld_res + col0;
-    if (full) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float4 b = __ldg(reinterpret_cast<const float4*>(r) + i);
-        v[4 * i + 0] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
-      }
-    } else {
-      for (int i = 0; i < ncols; ++i) v[i] += r[i];
-    }
-  }
-  if (first_split && e.res1) {
-    const float* r = e.res1 + (size_t)row * e.ld_res + col0;
-    if (full) {
+  for (int which = 0; which < 2; ++which) {
+    const float* rp = which == 0 ? e.res0 : e.res1;
+    if (first_split && rp) {
+      const float* r = rp + (size_t)row * e.ld_res + col0;
+      if (full) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float4 b = __ldg(reinterpret_cast<const float4*>(r) + i);
-        v[4 * i + 0] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+        for (int i = 0; i < 8; ++i) {
+          float4 b = __ldg(reinterpret_cast<const float4*>(r) + i);
+          v[4 * i + 0] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+        }
+      } else {
+        for (int i = 0; i < ncols; ++i) v[i] += r[i];
       }
-    } else {
-      for (int i = 0; i < ncols; ++i) v[i] += r[i];
     }
   }
   if (e.out_f32) {
@@ -139,28 +149,74 @@ __device__ __forceinline__ void epilogue_row32(const GemmParams& p, int row, int
   }
 }
 
+// ---- swizzled slab row access (thread == tile row r) ----
+// fp32 slab: [128][128B], TMA SWIZZLE_128B: 16-byte unit u of row r lives at r*128 + ((u ^ (r & 7)) << 4).
+__device__ __forceinline__ void slab_f32_add(const uint8_t* slab, int r, float (&v)[32]) {
+  const uint8_t* row = slab + r * 128;
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const float4 x = *reinterpret_cast<const float4*>(row + ((u ^ (r & 7)) << 4));
+    v[4 * u] += x.x; v[4 * u + 1] += x.y; v[4 * u + 2] += x.z; v[4 * u + 3] += x.w;
+  }
+}
+__device__ __forceinline__ void slab_f32_store(uint8_t* slab, int r, const float (&v)[32]) {
+  uint8_t* row = slab + r * 128;
+#pragma unroll
+  for (int u = 0; u < 8; ++u)
+    *reinterpret_cast<float4*>(row + ((u ^ (r & 7)) << 4)) = make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+}
+// bf16 slab: [128][64B], TMA SWIZZLE_64B: unit u (of 4) of row r lives at r*64 + ((u ^ ((r >> 1) & 3)) << 4).
+__device__ __forceinline__ void slab_bf16_load(const uint8_t* slab, int r, float (&x)[32]) {
+  const uint8_t* row = slab + r * 64;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const uint4 w = *reinterpret_cast<const uint4*>(row + ((u ^ ((r >> 1) & 3)) << 4));
+    const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = unpack_bf16x2(ww[j]);
+      x[8 * u + 2 * j] = f.x;
+      x[8 * u + 2 * j + 1] = f.y;
+    }
+  }
+}
+__device__ __forceinline__ void slab_bf16_store(uint8_t* slab, int r, const float (&v)[32]) {
+  uint8_t* row = slab + r * 64;
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+    *reinterpret_cast<uint4*>(row + ((u ^ ((r >> 1) & 3)) << 4)) =
+        make_uint4(pack_bf16x2(v[8 * u], v[8 * u + 1]), pack_bf16x2(v[8 * u + 2], v[8 * u + 3]),
+                   pack_bf16x2(v[8 * u + 4], v[8 * u + 5]), pack_bf16x2(v[8 * u + 6], v[8 * u + 7]));
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
 // ------------------------------------------------------------------------------------------------
 // tcgen05 kernel
 // ------------------------------------------------------------------------------------------------
-template <int BN, int STAGES, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(256, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ EpiMaps em, const GemmParams p) {
   constexpr int B_STAGE_BYTES = BN * BK * 2;
   constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  constexpr int ACC_STAGES = (2 * BN <= 512) ? 2 : 1;
+  constexpr int ACC_STAGES = 2;
   constexpr int TMEM_COLS = (ACC_STAGES * BN <= 32) ? 32
                             : (ACC_STAGES * BN <= 64) ? 64
                             : (ACC_STAGES * BN <= 128) ? 128
                             : (ACC_STAGES * BN <= 256) ? 256 : 512;
+  constexpr int MAX_STAGES = 8;
 
   extern __shared__ uint8_t smem_raw[];
   // 128B swizzle atoms need 1024-byte aligned stage bases.
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tfull_bar = empty_bar + STAGES;
+  const int STAGES = p.stages;
+  uint8_t* epi_smem = smem + STAGES * STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_smem + 2 * p.epi_stage_bytes);
+  uint64_t* empty_bar = full_bar + MAX_STAGES;
+  uint64_t* tfull_bar = empty_bar + MAX_STAGES;
   uint64_t* tempty_bar = tfull_bar + ACC_STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + ACC_STAGES);
+  uint64_t* in_full = tempty_bar + ACC_STAGES;  // [2] epilogue input slabs landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(in_full + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -178,6 +234,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], 4);  // one arrive per epilogue warp
     }
+    mbar_init(&in_full[0], 1);
+    mbar_init(&in_full[1], 1);
     fence_barrier_init();
     fence_proxy_async_smem();
   }
@@ -265,8 +323,36 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp >= 4) {
     // ===================== epilogue =====================
     const int ew = warp - 4;  // == warp % 4 -> TMEM lanes [32*ew, 32*ew+32)
+    const int r = ew * 32 + lane;  // row inside the tile
+    const bool leader = (r == 0);
+    const pg_gemm_epilogue& e = p.epi;
+    constexpr int NCH = BN / 32;
     int as = 0;
     uint32_t aph = 0;
+    unsigned gc = 0;  // global chunk counter (staged path): stage = gc & 1
+
+    auto issue_inputs = [&](int tile, int c, int st) {  // leader only
+      const int n_blk = tile % p.num_n_blk;
+      const int m_blk = (tile / p.num_n_blk) % p.num_m_blk;
+      uint8_t* base = epi_smem + st * p.epi_stage_bytes;
+      const int col0 = n_blk * BN + c * 32, row0 = m_blk * BM;
+      mbar_arrive_expect_tx(&in_full[st], p.in_bytes);
+      if (p.off_res0 >= 0) tma_load_2d(base + p.off_res0, &em.res0, &in_full[st], col0, row0);
+      if (p.off_res1 >= 0) tma_load_2d(base + p.off_res1, &em.res1, &in_full[st], col0, row0);
+      if (p.off_aux >= 0) tma_load_2d(base + p.off_aux, &em.aux, &in_full[st], col0, row0);
+    };
+    // chunk `ahead` positions after chunk c of `tile` in this CTA's tile sequence -> TMA its inputs into stage st
+    auto prefetch_inputs = [&](int tile, int c, int ahead, int st) {
+      int idx = c + ahead, t = tile;
+      while (idx >= NCH) { idx -= NCH; t += gridDim.x; }
+      if (t < num_tiles) issue_inputs(t, idx, st);
+    };
+    if (p.staged && p.in_bytes > 0 && leader) {
+      prefetch_inputs(blockIdx.x, 0, 0, 0);
+      prefetch_inputs(blockIdx.x, 0, 1, 1);
+    }
+    __syncwarp();
+
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int n_blk = tile % p.num_n_blk;
       const int rest = tile / p.num_n_blk;
@@ -274,20 +360,93 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int ks = rest / p.num_m_blk;
       mbar_wait(&tfull_bar[as], aph);
       tc_fence_after();
-      const int row = m_blk * BM + ew * 32 + lane;
+      const int row = m_blk * BM + r;
+      if (!p.staged) {
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t acc[32];
-        tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * BN + c * 32, acc);
-        tmem_wait_ld();
-        const int col0 = n_blk * BN + c * 32;
-        if (row < p.M && col0 < p.N) epilogue_row32(p, row, col0, min(32, p.N - col0), ks == 0, acc);
+        for (int c = 0; c < NCH; ++c) {
+          uint32_t acc[32];
+          tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * BN + c * 32, acc);
+          tmem_wait_ld();
+          const int col0 = n_blk * BN + c * 32;
+          if (row < p.M && col0 < p.N) epilogue_row32(p, row, col0, min(32, p.N - col0), ks == 0, acc);
+        }
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < NCH; ++c, ++gc) {
+          const int st = gc & 1;
+          uint8_t* base = epi_smem + st * p.epi_stage_bytes;
+          const int col0 = n_blk * BN + c * 32;
+          uint32_t acc[32];
+          tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * BN + c * 32, acc);
+          tmem_wait_ld();
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]) * e.alpha;
+          if (e.bias) {
+            if (col0 + 32 <= p.N) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + col0) + i);
+                v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (col0 + i < p.N) v[i] += __ldg(e.bias + col0 + i);
+            }
+          }
+          if (p.in_bytes > 0) mbar_wait(&in_full[st], (gc >> 1) & 1);
+          if (p.off_aux >= 0) {
+            float x[32];
+            slab_bf16_load(base + p.off_aux, r, x);
+            if (e.dact == PG_ACT_GELU) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] *= pg_act_bwd(PG_ACT_GELU, x[i]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] *= pg_act_bwd(e.dact, x[i]);
+            }
+          }
+          if (p.off_res0 >= 0) slab_f32_add(base + p.off_res0, r, v);
+          if (p.off_res1 >= 0) slab_f32_add(base + p.off_res1, r, v);
+          // the TMA store that last read this stage's output slabs (2 chunks ago) must have drained them
+          if (leader) tma_store_wait_read<1>();
+          __syncwarp();  // bar.sync / tcgen05.ld are warp-aligned: reconverge after every leader-only section
+          epi_bar_sync();
+          if (p.off_outf >= 0) slab_f32_store(base + p.off_outf, r, v);
+          if (p.off_outp >= 0) slab_bf16_store(base + p.off_outp, r, v);
+          if (p.off_outb >= 0) {
+            if (e.act == PG_ACT_GELU) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = pg_act_fwd(PG_ACT_GELU, v[i]);
+            } else if (e.act == PG_ACT_RELU) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+            } else if (e.act != PG_ACT_NONE) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = pg_act_fwd(e.act, v[i]);
+            }
+            slab_bf16_store(base + p.off_outb, r, v);
+          }
+          fence_proxy_async_smem();
+          epi_bar_sync();
+          if (leader) {
+            const int row0 = m_blk * BM;
+            if (p.off_outf >= 0) tma_store_2d(&em.out_f32, base + p.off_outf, col0, row0);
+            if (p.off_outp >= 0) tma_store_2d(&em.out_pre, base + p.off_outp, col0, row0);
+            if (p.off_outb >= 0) tma_store_2d(&em.out_bf16, base + p.off_outb, col0, row0);
+            tma_store_commit();
+            if (p.in_bytes > 0) prefetch_inputs(tile, c, 2, st);  // refill this stage with the chunk two ahead
+          }
+          __syncwarp();
+        }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[as]);
       if (++as == ACC_STAGES) { as = 0; aph ^= 1; }
     }
+    if (p.staged && leader) tma_store_wait<0>();
   }
 
   tc_fence_before();
@@ -299,7 +458,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 // ------------------------------------------------------------------------------------------------
-// SIMT cross-check kernel (tests only): one thread per 1x32 output segment, same epilogue code.
+// SIMT cross-check kernel (tests only): one thread per 1x32 output segment, same epilogue arithmetic.
 // ------------------------------------------------------------------------------------------------
 __global__ void gemm_simt_kernel(const bf16* __restrict__ A, int a_mn, int64_t lda, const bf16* __restrict__ B,
                                  int b_mn, int64_t ldb, const GemmParams p) {
@@ -326,7 +485,7 @@ __global__ void gemm_simt_kernel(const bf16* __restrict__ A, int a_mn, int64_t l
   epilogue_row32(p, row, col0, ncols, true, accu);
 }
 
-template <int BN, int STAGES, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN>
 int launch_tc(const void* A, int64_t lda, const void* B, int64_t ldb, GemmParams& p, cudaStream_t stream) {
   CUtensorMap tmA, tmB;
   if (!A_MN) {
@@ -340,12 +499,43 @@ int launch_tc(const void* A, int64_t lda, const void* B, int64_t ldb, GemmParams
     if (pg_make_tmap_2d_bf16(&tmB, B, p.K, p.N, ldb, BK, 64)) return 1;
   }
   constexpr int STAGE_BYTES = A_STAGE_BYTES + BN * BK * 2;
-  constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-  auto kern = gemm_tc_kernel<BN, STAGES, A_MN, B_MN>;
-  PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+  const pg_gemm_epilogue& e = p.epi;
+  EpiMaps em;
+  memset(&em, 0, sizeof(em));
+  // ---- epilogue staging plan ----
+  p.off_res0 = p.off_res1 = p.off_aux = p.off_outf = p.off_outb = p.off_outp = -1;
+  p.in_bytes = 0;
+  p.epi_stage_bytes = 0;
+  p.staged = (p.vec_ok && !e.accumulate && p.splits == 1) ? 1 : 0;
+  if (p.staged) {
+    int off = 0;
+    auto add = [&](int& slot, int bytes) { slot = off; off += bytes; };
+    if (e.res0) { add(p.off_res0, SLAB_F32); p.in_bytes += SLAB_F32; }
+    if (e.res1) { add(p.off_res1, SLAB_F32); p.in_bytes += SLAB_F32; }
+    if (e.dact != PG_ACT_NONE) { add(p.off_aux, SLAB_BF16); p.in_bytes += SLAB_BF16; }
+    if (e.out_f32) add(p.off_outf, SLAB_F32);
+    if (e.out_pre) add(p.off_outp, SLAB_BF16);
+    if (e.out_bf16) add(p.off_outb, SLAB_BF16);
+    p.epi_stage_bytes = off;
+    if (e.res0 && pg_make_tmap_2d(&em.res0, e.res0, 4, p.M, p.N, e.ld_res, BM, 32, 128)) return 1;
+    if (e.res1 && pg_make_tmap_2d(&em.res1, e.res1, 4, p.M, p.N, e.ld_res, BM, 32, 128)) return 1;
+    if (e.dact != PG_ACT_NONE && pg_make_tmap_2d(&em.aux, e.aux, 2, p.M, p.N, e.ld_aux, BM, 32, 64)) return 1;
+    if (e.out_f32 && pg_make_tmap_2d(&em.out_f32, e.out_f32, 4, p.M, p.N, e.ld_out_f32, BM, 32, 128)) return 1;
+    if (e.out_pre && pg_make_tmap_2d(&em.out_pre, e.out_pre, 2, p.M, p.N, e.ld_out_pre, BM, 32, 64)) return 1;
+    if (e.out_bf16 && pg_make_tmap_2d(&em.out_bf16, e.out_bf16, 2, p.M, p.N, e.ld_out_bf16, BM, 32, 64)) return 1;
+  }
+  const int fixed = 2 * p.epi_stage_bytes + 1024 /*align slack*/ + 512 /*barriers*/;
+  int stages = (SMEM_LIMIT - fixed) / STAGE_BYTES;
+  if (stages > 8) stages = 8;
+  if (stages > p.k_iters + 1) stages = p.k_iters + 1 > 2 ? p.k_iters + 1 : 2;
+  PG_REQUIRE(stages >= 2, "pg_gemm_bf16: epilogue staging leaves no room for the operand pipeline (BN=%d)", BN);
+  p.stages = stages;
+  const int smem_bytes = stages * STAGE_BYTES + fixed;
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN>;
+  PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
   const int num_tiles = p.num_m_blk * p.num_n_blk * p.splits;
   const int grid = min(num_tiles, pg_num_sms());
-  kern<<<grid, 256, SMEM, stream>>>(tmA, tmB, p);
+  kern<<<grid, 256, smem_bytes, stream>>>(tmA, tmB, em, p);
   return pg_check_launch("pg_gemm_bf16(tcgen05)");
 }
 
@@ -358,14 +548,23 @@ int dispatch_bn(const void* A, int64_t lda, const void* B, int64_t ldb, GemmPara
   else if (p.N > 32) bn = 64;
   else bn = 32;
   if (B_MN && bn < 64) bn = 64;  // MN-major operands are staged in 64-wide swizzle atoms
-  // Narrow problems with few row blocks prefer 128 to create more tiles.
-  if (bn == 256 && ((p.M + BM - 1) / BM) * ((p.N + 255) / 256) * p.splits < pg_num_sms() && p.N % 256 != 0) bn = 128;
+  const pg_gemm_epilogue& e = p.epi;
+  if (bn == 256) {
+    // fp32-heavy staged epilogues (residual stream in/out) need more slab space than a 256-wide tile leaves
+    // next to a >= 3-deep operand pipeline; those GEMMs are HBM-bound anyway, so take the 128-wide tile.
+    const int epi = (e.res0 ? SLAB_F32 : 0) + (e.res1 ? SLAB_F32 : 0) + (e.dact != PG_ACT_NONE ? SLAB_BF16 : 0) +
+                    (e.out_f32 ? SLAB_F32 : 0) + (e.out_pre ? SLAB_BF16 : 0) + (e.out_bf16 ? SLAB_BF16 : 0);
+    const bool staged = p.vec_ok && !e.accumulate && p.splits == 1;
+    if (staged && (SMEM_LIMIT - 2 * epi - 1536) / (A_STAGE_BYTES + 256 * BK * 2) < 4) bn = 128;
+    // Narrow problems with few tiles prefer 128 to spread over more SMs.
+    if (bn == 256 && ((p.M + BM - 1) / BM) * ((p.N + 255) / 256) * p.splits < pg_num_sms() && p.N % 256 != 0) bn = 128;
+  }
   p.num_n_blk = (p.N + bn - 1) / bn;
   switch (bn) {
-    case 256: return launch_tc<256, 4, A_MN, B_MN>(A, lda, B, ldb, p, stream);
-    case 128: return launch_tc<128, 6, A_MN, B_MN>(A, lda, B, ldb, p, stream);
-    case 64: return launch_tc<64, 8, A_MN, B_MN>(A, lda, B, ldb, p, stream);
-    default: return launch_tc<32, 8, A_MN, B_MN>(A, lda, B, ldb, p, stream);
+    case 256: return launch_tc<256, A_MN, B_MN>(A, lda, B, ldb, p, stream);
+    case 128: return launch_tc<128, A_MN, B_MN>(A, lda, B, ldb, p, stream);
+    case 64: return launch_tc<64, A_MN, B_MN>(A, lda, B, ldb, p, stream);
+    default: return launch_tc<32, A_MN, B_MN>(A, lda, B, ldb, p, stream);
   }
 }
 
@@ -385,6 +584,7 @@ extern "C" int pg_gemm_bf16(const void* A, int a_mn_major, int64_t lda, const vo
     PG_REQUIRE(epi->accumulate && epi->out_f32 && !epi->out_bf16 && !epi->out_pre && epi->dact == PG_ACT_NONE,
                "pg_gemm_bf16: split_k > 1 requires accumulate=1 into out_f32 only");
   GemmParams p;
+  memset(&p, 0, sizeof(p));
   p.M = M; p.N = N; p.K = K;
   p.num_m_blk = (M + BM - 1) / BM;
   p.num_n_blk = 0;

@@ -61,11 +61,13 @@ static PFN_encodeTiled get_encode() {
   return fn;
 }
 
-int pg_make_tmap_nd_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
-                         const uint64_t* strides_bytes, const uint32_t* box, int swizzle128) {
+// Generic tiled map.  elem_bytes in {2 (bf16), 4 (fp32)}; swizzle_bytes in {0, 32, 64, 128}.
+int pg_make_tmap_nd(CUtensorMap* out, const void* base, int elem_bytes, int rank, const uint64_t* dims,
+                    const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes) {
   PFN_encodeTiled enc = get_encode();
   PG_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
   PG_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base pointer %p not 16-byte aligned", base);
+  PG_REQUIRE(elem_bytes == 2 || elem_bytes == 4, "TMA element size %d unsupported", elem_bytes);
   cuuint64_t gdim[5];
   cuuint64_t gstr[4];
   cuuint32_t bx[5];
@@ -81,19 +83,34 @@ int pg_make_tmap_nd_bf16(CUtensorMap* out, const void* base, int rank, const uin
     PG_REQUIRE((strides_bytes[i] & 15) == 0, "TMA stride %d = %llu bytes not a multiple of 16", i,
                (unsigned long long)strides_bytes[i]);
   }
-  if (swizzle128) PG_REQUIRE(box[0] * 2 <= 128, "TMA inner box %u bf16 exceeds the 128B swizzle span", box[0]);
-  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr,
-                   bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+  CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_NONE;
+  if (swizzle_bytes == 32) sw = CU_TENSOR_MAP_SWIZZLE_32B;
+  else if (swizzle_bytes == 64) sw = CU_TENSOR_MAP_SWIZZLE_64B;
+  else if (swizzle_bytes == 128) sw = CU_TENSOR_MAP_SWIZZLE_128B;
+  if (swizzle_bytes)
+    PG_REQUIRE((int)box[0] * elem_bytes <= swizzle_bytes, "TMA inner box %u x %dB exceeds the %dB swizzle span", box[0],
+               elem_bytes, swizzle_bytes);
+  CUresult r = enc(out, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+                   (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   PG_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   return 0;
 }
 
+int pg_make_tmap_nd_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                         const uint64_t* strides_bytes, const uint32_t* box, int swizzle128) {
+  return pg_make_tmap_nd(out, base, 2, rank, dims, strides_bytes, box, swizzle128 ? 128 : 0);
+}
+
+int pg_make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t rows, uint64_t cols, uint64_t ld,
+                    uint32_t box_rows, uint32_t box_cols, int swizzle_bytes) {
+  uint64_t dims[2] = {cols, rows};
+  uint64_t strides[1] = {ld * (uint64_t)elem_bytes};
+  uint32_t box[2] = {box_cols, box_rows};
+  return pg_make_tmap_nd(out, base, elem_bytes, 2, dims, strides, box, swizzle_bytes);
+}
+
 int pg_make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
                          uint32_t box_rows, uint32_t box_cols) {
-  uint64_t dims[2] = {cols, rows};
-  uint64_t strides[1] = {ld * 2};
-  uint32_t box[2] = {box_cols, box_rows};
-  return pg_make_tmap_nd_bf16(out, base, 2, dims, strides, box, 1);
+  return pg_make_tmap_2d(out, base, 2, rows, cols, ld, box_rows, box_cols, 128);
 }
