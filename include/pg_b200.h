@@ -87,14 +87,16 @@ int pg_colsum_f32(const float* x, int64_t ld, int P, int C, float* out, int accu
  * biased variance; mean/rstd [P] fp32 are saved for backward.
  * Backward: dx = rstd * (g - mean_c(g) - xhat * mean_c(g * xhat)), g = dy * gamma;
  *   dx_out_f32 = dx + dres0 + dres1 (fused residual-gradient adds), optional bf16 copy for the next
- *   dgrad GEMM; dgamma/dbeta are accumulated (atomics) into fp32 [C] buffers that the caller zeroed.
+ *   dgrad GEMM; dgamma/dbeta are accumulated (atomics) into fp32 [C] buffers that the caller zeroed;
+ *   dx_colsum (optional, [C], caller-zeroed) receives the column sums of dx_out = the bias gradient of the
+ *   layer whose output x is (saves a separate pass over the gradient).
  * ------------------------------------------------------------------------------------------- */
 int pg_layernorm_fwd(const float* x, const float* gamma, const float* beta, int P, int C, float eps,
                      void* y_bf16, float* y_f32, float* mean, float* rstd, void* stream);
 int pg_layernorm_bwd(const void* dy_bf16, const float* dy_f32, const float* x, const float* gamma,
                      const float* mean, const float* rstd, int P, int C, const float* dres0,
                      const float* dres1, float* dx_f32, void* dx_bf16, float* dgamma, float* dbeta,
-                     void* stream);
+                     float* dx_colsum, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * GatedActivation — reference nn/convolution.py:46-66: act(x[:, :C]) * sigmoid(x[:, C:]).

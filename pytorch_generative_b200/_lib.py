@@ -39,7 +39,7 @@ _SIGNATURES = {
     "pg_colsum_bf16": [_vp, _i64, _i32, _i32, _vp, _i32, _vp],
     "pg_colsum_f32": [_vp, _i64, _i32, _i32, _vp, _i32, _vp],
     "pg_layernorm_fwd": [_vp, _vp, _vp, _i32, _i32, _f32, _vp, _vp, _vp, _vp, _vp],
-    "pg_layernorm_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "pg_layernorm_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "pg_gated_act_fwd": [_vp, _i32, _i32, _i32, _i32, _vp, _i32, _vp],
     "pg_gated_act_bwd": [_vp, _i32, _vp, _i32, _i32, _i32, _i32, _vp, _i32, _vp],
     "pg_bce_logits_fwd_bwd": [_vp, _vp, _i64, _f32, _vp, _vp, _vp],
@@ -195,14 +195,15 @@ def layernorm_fwd(x, gamma, beta, eps, y_bf16=None, y_f32=None, mean=None, rstd=
 
 
 def layernorm_bwd(dy, x, gamma, mean, rstd, dres0=None, dres1=None, dx_f32=None, dx_bf16=None, dgamma=None,
-                  dbeta=None):
+                  dbeta=None, dx_colsum=None):
     lib = load()
     P, C = x.shape
     assert dy.is_contiguous() and x.is_contiguous()
     dy_b = _ptr(dy) if dy.dtype == torch.bfloat16 else None
     dy_f = _ptr(dy) if dy.dtype == torch.float32 else None
     _check(lib.pg_layernorm_bwd(dy_b, dy_f, _ptr(x), _ptr(gamma), _ptr(mean), _ptr(rstd), P, C, _ptr(dres0),
-                                _ptr(dres1), _ptr(dx_f32), _ptr(dx_bf16), _ptr(dgamma), _ptr(dbeta), _stream()),
+                                _ptr(dres1), _ptr(dx_f32), _ptr(dx_bf16), _ptr(dgamma), _ptr(dbeta), _ptr(dx_colsum),
+                                _stream()),
            "pg_layernorm_bwd")
 
 

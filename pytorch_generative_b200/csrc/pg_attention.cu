@@ -70,8 +70,37 @@ __global__ void __launch_bounds__(128) attn_fwd_simt(const AttnArgs a) {
   if (lane == 0 && a.lse) a.lse[((size_t)n * a.H + h) * a.S + i] = nkeys > 0 ? m + __logf(l) : 0.f;
 }
 
-// delta[n,h,i] = sum_d dO[i,d] * O[i,d]
+// delta[n,h,i] = sum_d dO[i,d] * O[i,d].  16-byte loads: (dv/8) consecutive lanes cover one (row, head) slot, so a
+// warp reads 512 contiguous bytes of each tensor per step.
 __global__ void attn_delta_kernel(const AttnArgs a) {
+  const int lanes_per = a.dv / 8;  // lanes per (row, head): 8 for dv=64, 16 for dv=128 (dv % 8 == 0, dv <= 256)
+  const long long total = (long long)a.N * a.S * a.H * lanes_per;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int sub = (int)(idx % lanes_per);
+    const long long rh = idx / lanes_per;
+    const int h = (int)(rh % a.H);
+    const long long row = rh / a.H;  // n * S + i
+    const uint4 x = *reinterpret_cast<const uint4*>(a.d_o + row * a.ld_do + h * a.dv + sub * 8);
+    const uint4 y = *reinterpret_cast<const uint4*>(a.o + row * a.ld_o + h * a.dv + sub * 8);
+    const uint32_t xw[4] = {x.x, x.y, x.z, x.w}, yw[4] = {y.x, y.y, y.z, y.w};
+    float s = 0.f;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const float2 p = unpack_bf16x2(xw[t]), q = unpack_bf16x2(yw[t]);
+      s = fmaf(p.x, q.x, fmaf(p.y, q.y, s));
+    }
+    // reduce over the lanes_per consecutive lanes of this slot (lanes_per is a power of two <= 32)
+    for (int o = lanes_per >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (sub == 0) {
+      const int n = (int)(row / a.S), i = (int)(row % a.S);
+      a.delta[((size_t)n * a.H + h) * a.S + i] = s;
+    }
+  }
+}
+
+// Generic fallback (any dv): one warp per (row, head).
+__global__ void attn_delta_generic_kernel(const AttnArgs a) {
   const int lane = threadIdx.x & 31;
   const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long total = (long long)a.N * a.H * a.S;
@@ -214,7 +243,15 @@ extern "C" int pg_causal_attn_bwd(const void* q, int64_t ld_q, const void* k, in
   a.scale = scale;
   a.dq_accum = dq_accum;
   const long long total = (long long)N * H * S;
-  attn_delta_kernel<<<(unsigned)((total * 32 + 255) / 256), 256, 0, stream>>>(a);
+  const int lanes_per = dv / 8;
+  const bool pow2 = dv % 8 == 0 && lanes_per >= 1 && lanes_per <= 32 && (lanes_per & (lanes_per - 1)) == 0;
+  if (pow2 && ld_o % 8 == 0 && ld_do % 8 == 0 && (total * lanes_per) % 32 == 0) {
+    long long blocks = (total * lanes_per + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    attn_delta_kernel<<<(unsigned)blocks, 256, 0, stream>>>(a);
+  } else {
+    attn_delta_generic_kernel<<<(unsigned)((total * 32 + 255) / 256), 256, 0, stream>>>(a);
+  }
   if (pg_check_launch("pg_causal_attn_bwd(delta)")) return 1;
   if (impl == 1) {
     PG_REQUIRE(S <= MAX_S && dk <= MAX_D && dv <= MAX_D, "pg_causal_attn_bwd(simt): S<=%d, d<=%d", MAX_S, MAX_D);

@@ -49,8 +49,19 @@ __device__ __forceinline__ uint64_t desc_mnmajor(uint32_t tile_addr, int kk) {
   return umma_desc_sw128(tile_addr + kk * 2048, ATOM_BYTES, 1024);
 }
 
+// fp32 slab [128 rows][32 floats] under the TMA 128B swizzle: 16-byte unit u of row r at r*128 + ((u ^ (r&7)) << 4).
+__device__ __forceinline__ void slab32_store_scaled(uint8_t* slab, int r, const uint32_t (&v)[32], float scale) {
+  uint8_t* row = slab + r * 128;
+#pragma unroll
+  for (int u = 0; u < 8; ++u)
+    *reinterpret_cast<float4*>(row + ((u ^ (r & 7)) << 4)) =
+        make_float4(__uint_as_float(v[4 * u]) * scale, __uint_as_float(v[4 * u + 1]) * scale,
+                    __uint_as_float(v[4 * u + 2]) * scale, __uint_as_float(v[4 * u + 3]) * scale);
+}
+__device__ __forceinline__ void attn_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
 struct AttnTmaps {
-  CUtensorMap q, k, v, d_o;
+  CUtensorMap q, k, v, d_o, dq;  // dq: fp32 accumulator [N][S][H*64], box {32, 128, 1}
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -361,6 +372,10 @@ attn_bwd_tc_kernel(const __grid_constant__ AttnTmaps tm, const AttnArgs a, const
       const bool need_mask = (it == 0) || (i == T - 1);
       mbar_wait(s_full, it & 1);
       tc_fence_after();
+      // sP doubles as the fp32 staging tile of the previous iteration's dQ reduce: it must have been read out
+      if (r == 0) tma_store_wait_read<0>();
+      __syncwarp();
+      attn_bar_sync();
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         uint32_t sv[32], dv[32];
@@ -389,22 +404,26 @@ attn_bwd_tc_kernel(const __grid_constant__ AttnTmaps tm, const AttnArgs a, const
       mbar_arrive(pds_full);
       mbar_wait(dq_full, it & 1);
       tc_fence_after();
+      // dQ_i tile -> fp32 slabs in sP (free: all MMAs of this iteration are complete) -> one bulk reduce-add
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         uint32_t v[32];
         tmem_ld_32x32b_x32(tmem + COL_DQ + lane_base + c * 32, v);
         tmem_wait_ld();
-        if (row_ok) {
-          float* dst = a.dq_accum + ((size_t)n * a.S + qi) * ((size_t)a.H * 64) + h * 64 + c * 32;
-#pragma unroll
-          for (int e = 0; e < 32; e += 4)
-            atomicAdd(reinterpret_cast<float4*>(dst + e),
-                      make_float4(__uint_as_float(v[e]) * a.scale, __uint_as_float(v[e + 1]) * a.scale,
-                                  __uint_as_float(v[e + 2]) * a.scale, __uint_as_float(v[e + 3]) * a.scale));
-        }
+        slab32_store_scaled(sP + c * ATOM_BYTES, r, v, a.scale);
       }
+      fence_proxy_async_smem();
+      attn_bar_sync();
+      if (r == 0) {
+        tma_reduce_add_3d(&tm.dq, sP, h * 64, i * AT, n);
+        tma_reduce_add_3d(&tm.dq, sP + ATOM_BYTES, h * 64 + 32, i * AT, n);
+        tma_store_commit();
+      }
+      __syncwarp();
       tc_fence_before();
     }
+    if (r == 0) tma_store_wait<0>();
+    __syncwarp();
     // dV_j, dK_j are complete (the last dq_full commit covers all earlier MMAs); thread == key row.
     // TMEM loads are warp-aligned instructions: every lane executes them, only the stores are predicated.
     const int kj = k0 + r;
@@ -509,6 +528,12 @@ int attn_bwd_tc(const AttnArgs& a, cudaStream_t stream) {
   if (make_attn_map(&tm.k, a.k, a.ld_k, a.H * 64, a.S, a.N)) return 1;
   if (make_attn_map(&tm.v, a.v, a.ld_v, a.H * a.dv, a.S, a.N)) return 1;
   if (make_attn_map(&tm.d_o, a.d_o, a.ld_do, a.H * a.dv, a.S, a.N)) return 1;
+  {
+    uint64_t dims[3] = {(uint64_t)a.H * 64, (uint64_t)a.S, (uint64_t)a.N};
+    uint64_t strides[2] = {(uint64_t)a.H * 64 * 4, (uint64_t)a.S * a.H * 64 * 4};
+    uint32_t box[3] = {32, (uint32_t)AT, 1};
+    if (pg_make_tmap_nd(&tm.dq, a.dq_accum, 4, 3, dims, strides, box, 128)) return 1;
+  }
   const int T = (a.S + AT - 1) / AT;
   const unsigned grid = (unsigned)(a.N * a.H * T);
   if (a.dv == 64) {

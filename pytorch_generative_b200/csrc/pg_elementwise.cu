@@ -7,6 +7,38 @@
 
 namespace {
 
+// ---- 8-element vector load/store helpers (fp32: 2x16B, bf16: 1x16B) ----
+template <typename T>
+__device__ __forceinline__ void load8(const T* p, float (&v)[8]);
+template <>
+__device__ __forceinline__ void load8<float>(const float* p, float (&v)[8]) {
+  const float4 a = __ldcs(reinterpret_cast<const float4*>(p)), b = __ldcs(reinterpret_cast<const float4*>(p) + 1);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+template <>
+__device__ __forceinline__ void load8<bf16>(const bf16* p, float (&v)[8]) {
+  const uint4 u = __ldcs(reinterpret_cast<const uint4*>(p));
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = unpack_bf16x2(w[i]);
+    v[2 * i] = f.x;
+    v[2 * i + 1] = f.y;
+  }
+}
+template <typename T>
+__device__ __forceinline__ void store8(T* p, const float (&v)[8]);
+template <>
+__device__ __forceinline__ void store8<float>(float* p, const float (&v)[8]) {
+  __stcs(reinterpret_cast<float4*>(p), make_float4(v[0], v[1], v[2], v[3]));
+  __stcs(reinterpret_cast<float4*>(p) + 1, make_float4(v[4], v[5], v[6], v[7]));
+}
+template <>
+__device__ __forceinline__ void store8<bf16>(bf16* p, const float (&v)[8]) {
+  *reinterpret_cast<uint4*>(p) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                                            pack_bf16x2(v[6], v[7]));
+}
+
 // ------------------------------------------------------------------------------------------------
 // LayerNorm over the channel dim of a pixel-major [P, C] fp32 matrix (reference nn/convolution.py:69-75).
 // Fast path: C = 128 * V, one warp per row, the row lives in registers (V float4 per lane).
@@ -99,7 +131,8 @@ __global__ void __launch_bounds__(256)
 ln_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x, const float* __restrict__ gamma,
               const float* __restrict__ mean_in, const float* __restrict__ rstd_in, int P,
               const float* __restrict__ dres0, const float* __restrict__ dres1, float* __restrict__ dx_f32,
-              bf16* __restrict__ dx_bf16, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+              bf16* __restrict__ dx_bf16, float* __restrict__ dgamma, float* __restrict__ dbeta,
+              float* __restrict__ dx_colsum) {
   constexpr int C = 128 * V;
   __shared__ float red[8][33];
   const int lane = threadIdx.x & 31;
@@ -107,12 +140,13 @@ ln_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x, const f
   const int warps_per_block = blockDim.x >> 5;
   const int warp_global = blockIdx.x * warps_per_block + wib;
   const int num_warps = gridDim.x * warps_per_block;
-  float4 g[V], dg[V], db[V];
+  float4 g[V], dg[V], db[V], ds[V];
 #pragma unroll
   for (int i = 0; i < V; ++i) {
     g[i] = __ldg(reinterpret_cast<const float4*>(gamma) + i * 32 + lane);
     dg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    ds[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   for (int row = warp_global; row < P; row += num_warps) {
     const float mean = __ldg(mean_in + row);
@@ -157,18 +191,21 @@ ln_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x, const f
         const float4 r = __ldcs(reinterpret_cast<const float4*>(dres1) + off);
         o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
       }
+      ds[i].x += o.x; ds[i].y += o.y; ds[i].z += o.z; ds[i].w += o.w;
       if (dx_f32) __stcs(reinterpret_cast<float4*>(dx_f32) + off, o);
       if (dx_bf16) reinterpret_cast<uint2*>(dx_bf16)[off] = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
     }
   }
-  // Block reduction of dgamma / dbeta partials: for each float4 slot, transpose through shared memory.
-  if (dgamma || dbeta) {
+  // Block reduction of the per-lane column partials (dgamma, dbeta, column sums of the emitted gradient = the
+  // bias gradient of the layer that produced x): transpose through shared memory, one atomic per column.
+  if (dgamma || dbeta || dx_colsum) {
 #pragma unroll
     for (int i = 0; i < V; ++i) {
 #pragma unroll
-      for (int which = 0; which < 2; ++which) {
-        const float4 val = which == 0 ? dg[i] : db[i];
-        float* dst = which == 0 ? dgamma : dbeta;
+      for (int which = 0; which < 3; ++which) {
+        const float4 val = which == 0 ? dg[i] : (which == 1 ? db[i] : ds[i]);
+        float* dst = which == 0 ? dgamma : (which == 1 ? dbeta : dx_colsum);
+        if (dst == nullptr) continue;  // uniform across the block
         const float comp[4] = {val.x, val.y, val.z, val.w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -192,7 +229,7 @@ __global__ void ln_bwd_generic_kernel(const void* __restrict__ dy_, const float*
                                       const float* __restrict__ rstd_in, int P, int C, const float* __restrict__ dres0,
                                       const float* __restrict__ dres1, float* __restrict__ dx_f32,
                                       bf16* __restrict__ dx_bf16, float* __restrict__ dgamma,
-                                      float* __restrict__ dbeta) {
+                                      float* __restrict__ dbeta, float* __restrict__ dx_colsum) {
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= P) return;
@@ -218,6 +255,7 @@ __global__ void ln_bwd_generic_kernel(const void* __restrict__ dy_, const float*
     const size_t off = (size_t)row * C + c;
     if (dres0) o += dres0[off];
     if (dres1) o += dres1[off];
+    if (dx_colsum) atomicAdd(dx_colsum + c, o);
     if (dx_f32) dx_f32[off] = o;
     if (dx_bf16) dx_bf16[off] = __float2bfloat16(o);
   }
@@ -226,36 +264,6 @@ __global__ void ln_bwd_generic_kernel(const void* __restrict__ dy_, const float*
 // ------------------------------------------------------------------------------------------------
 // GatedActivation (reference nn/convolution.py:62-66).  8 channels per thread.
 // ------------------------------------------------------------------------------------------------
-template <typename T>
-__device__ __forceinline__ void load8(const T* p, float (&v)[8]);
-template <>
-__device__ __forceinline__ void load8<float>(const float* p, float (&v)[8]) {
-  const float4 a = __ldcs(reinterpret_cast<const float4*>(p)), b = __ldcs(reinterpret_cast<const float4*>(p) + 1);
-  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-}
-template <>
-__device__ __forceinline__ void load8<bf16>(const bf16* p, float (&v)[8]) {
-  const uint4 u = __ldcs(reinterpret_cast<const uint4*>(p));
-  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float2 f = unpack_bf16x2(w[i]);
-    v[2 * i] = f.x;
-    v[2 * i + 1] = f.y;
-  }
-}
-template <typename T>
-__device__ __forceinline__ void store8(T* p, const float (&v)[8]);
-template <>
-__device__ __forceinline__ void store8<float>(float* p, const float (&v)[8]) {
-  __stcs(reinterpret_cast<float4*>(p), make_float4(v[0], v[1], v[2], v[3]));
-  __stcs(reinterpret_cast<float4*>(p) + 1, make_float4(v[4], v[5], v[6], v[7]));
-}
-template <>
-__device__ __forceinline__ void store8<bf16>(bf16* p, const float (&v)[8]) {
-  *reinterpret_cast<uint4*>(p) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
-                                            pack_bf16x2(v[6], v[7]));
-}
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
 
 template <typename TX, typename TY>
@@ -322,8 +330,42 @@ __global__ void bce_kernel(const float* __restrict__ logits, const float* __rest
 }
 
 // ------------------------------------------------------------------------------------------------
-// Column sums (bias gradients): block = 32x8 threads over a strip of rows, coalesced along columns.
+// Column sums (bias gradients).  Fast path: each thread owns 8 consecutive columns (16-byte loads for bf16,
+// 2x16 for fp32), a warp covers 256 columns of one row per step, 8 warps stride over the rows of the block's
+// strip; partial sums meet in shared memory, one atomic per column per block.
 // ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+colsum_vec_kernel(const T* __restrict__ x, int64_t ld, int P, int C, int rows_per_block, float* __restrict__ out) {
+  __shared__ float red[8][256 + 8];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int col = blockIdx.x * 256 + lane * 8;
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(r0 + rows_per_block, P);
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  if (col < C) {  // C % 8 == 0 on this path
+    for (int r = r0 + w; r < r1; r += 8) {
+      float v[8];
+      load8<T>(x + (size_t)r * ld + col, v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += v[i];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[w][lane * 8 + i] = acc[i];
+  __syncthreads();
+  const int c = threadIdx.x;  // 256 threads <-> 256 columns of the block
+  if (blockIdx.x * 256 + c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][c];
+    atomicAdd(out + blockIdx.x * 256 + c, t);
+  }
+}
+
+// Generic fallback: block = 32x8 threads over a strip of rows, coalesced along columns.
 template <typename T>
 __global__ void colsum_kernel(const T* __restrict__ x, int64_t ld, int P, int C, int rows_per_block,
                               float* __restrict__ out) {
@@ -433,7 +475,7 @@ extern "C" int pg_layernorm_fwd(const float* x, const float* gamma, const float*
 extern "C" int pg_layernorm_bwd(const void* dy_bf16, const float* dy_f32, const float* x, const float* gamma,
                                 const float* mean, const float* rstd, int P, int C, const float* dres0,
                                 const float* dres1, float* dx_f32, void* dx_bf16, float* dgamma, float* dbeta,
-                                void* stream_) {
+                                float* dx_colsum, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   PG_REQUIRE((dy_bf16 != nullptr) != (dy_f32 != nullptr), "pg_layernorm_bwd: exactly one of dy_bf16 / dy_f32");
   PG_REQUIRE(x && gamma && mean && rstd && (dx_f32 || dx_bf16), "pg_layernorm_bwd: null argument");
@@ -447,10 +489,10 @@ extern "C" int pg_layernorm_bwd(const void* dy_bf16, const float* dy_f32, const 
   case V:                                                                                                        \
     if (dy_bf16)                                                                                                 \
       ln_bwd_kernel<V, true><<<blocks, threads, 0, stream>>>(dy_bf16, x, gamma, mean, rstd, P, dres0, dres1, dx_f32, \
-                                                             dxb, dgamma, dbeta);                                \
+                                                             dxb, dgamma, dbeta, dx_colsum);                     \
     else                                                                                                         \
       ln_bwd_kernel<V, false><<<blocks, threads, 0, stream>>>(dy_f32, x, gamma, mean, rstd, P, dres0, dres1, dx_f32, \
-                                                              dxb, dgamma, dbeta);                               \
+                                                              dxb, dgamma, dbeta, dx_colsum);                    \
     break;
       LNB_CASE(1) LNB_CASE(2) LNB_CASE(3) LNB_CASE(4) LNB_CASE(5) LNB_CASE(6) LNB_CASE(7) LNB_CASE(8)
 #undef LNB_CASE
@@ -459,10 +501,10 @@ extern "C" int pg_layernorm_bwd(const void* dy_bf16, const float* dy_f32, const 
     const int blocks = (P + wpb - 1) / wpb;
     if (dy_bf16)
       ln_bwd_generic_kernel<true><<<blocks, threads, 0, stream>>>(dy_bf16, x, gamma, mean, rstd, P, C, dres0, dres1,
-                                                                  dx_f32, dxb, dgamma, dbeta);
+                                                                  dx_f32, dxb, dgamma, dbeta, dx_colsum);
     else
       ln_bwd_generic_kernel<false><<<blocks, threads, 0, stream>>>(dy_f32, x, gamma, mean, rstd, P, C, dres0, dres1,
-                                                                   dx_f32, dxb, dgamma, dbeta);
+                                                                   dx_f32, dxb, dgamma, dbeta, dx_colsum);
   }
   return pg_check_launch("pg_layernorm_bwd");
 }
@@ -515,18 +557,30 @@ extern "C" int pg_colsum_bf16(const void* x, int64_t ld, int P, int C, float* ou
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   PG_REQUIRE(x && out && P > 0 && C > 0, "pg_colsum_bf16: null/empty argument");
   if (!accumulate) PG_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * C, stream));
-  const int rows_per_block = 512;
-  dim3 grid((C + 31) / 32, (P + rows_per_block - 1) / rows_per_block), block(32, 8);
-  colsum_kernel<bf16><<<grid, block, 0, stream>>>((const bf16*)x, ld, P, C, rows_per_block, out);
+  if (C % 8 == 0 && ld % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    const int rows_per_block = 256;
+    dim3 grid((C + 255) / 256, (P + rows_per_block - 1) / rows_per_block);
+    colsum_vec_kernel<bf16><<<grid, 256, 0, stream>>>((const bf16*)x, ld, P, C, rows_per_block, out);
+  } else {
+    const int rows_per_block = 512;
+    dim3 grid((C + 31) / 32, (P + rows_per_block - 1) / rows_per_block), block(32, 8);
+    colsum_kernel<bf16><<<grid, block, 0, stream>>>((const bf16*)x, ld, P, C, rows_per_block, out);
+  }
   return pg_check_launch("pg_colsum_bf16");
 }
 extern "C" int pg_colsum_f32(const float* x, int64_t ld, int P, int C, float* out, int accumulate, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   PG_REQUIRE(x && out && P > 0 && C > 0, "pg_colsum_f32: null/empty argument");
   if (!accumulate) PG_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * C, stream));
-  const int rows_per_block = 512;
-  dim3 grid((C + 31) / 32, (P + rows_per_block - 1) / rows_per_block), block(32, 8);
-  colsum_kernel<float><<<grid, block, 0, stream>>>(x, ld, P, C, rows_per_block, out);
+  if (C % 8 == 0 && ld % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    const int rows_per_block = 256;
+    dim3 grid((C + 255) / 256, (P + rows_per_block - 1) / rows_per_block);
+    colsum_vec_kernel<float><<<grid, 256, 0, stream>>>(x, ld, P, C, rows_per_block, out);
+  } else {
+    const int rows_per_block = 512;
+    dim3 grid((C + 31) / 32, (P + rows_per_block - 1) / rows_per_block), block(32, 8);
+    colsum_kernel<float><<<grid, block, 0, stream>>>(x, ld, P, C, rows_per_block, out);
+  }
   return pg_check_launch("pg_colsum_f32");
 }
 

@@ -121,7 +121,10 @@ class _ImageGPTStack(torch.autograd.Function):
         ops.linear_wgrad(dl, sv["af"], dwo)
         grads[-2] = dwo[:cout].reshape(cout, C, 1, 1)
         daf = ops.linear_dgrad(dl[:, :cout], sv["wo"])
-        dx, dx_b, grads[-4], grads[-3] = ops.layernorm_bwd(daf, sv["xs_final"], ln_w.detach(), sv["mean_f"], sv["rstd_f"])
+        # every LayerNorm backward also emits the column sums of the gradient it writes = the bias gradient of the
+        # linear layer that produced its input (fc2 of the block above / the attention projection)
+        dx, dx_b, grads[-4], grads[-3], dx_sum = ops.layernorm_bwd(daf, sv["xs_final"], ln_w.detach(), sv["mean_f"],
+                                                                    sv["rstd_f"], want_colsum=True)
         del daf
 
         for b in reversed(range(n_blocks)):
@@ -130,7 +133,7 @@ class _ImageGPTStack(torch.autograd.Function):
             (ln1_w, _, q_w, _, kv_w, _, p_w, _, ln2_w, _, f1_w, _, f2_w, _) = params[base_i: base_i + PARAMS_PER_BLOCK]
             meta, dv_slot = blk["meta"], blk["meta"]["dv_slot"]
             # x_new = x + h + fc2(gelu(fc1(ln2(h))))
-            grads[base_i + 13] = ops.bias_grad(dx)
+            grads[base_i + 13] = dx_sum
             dw2 = torch.zeros(C, 4 * C, dtype=F32, device=dev)
             ops.linear_wgrad(dx_b, blk["g"], dw2)
             grads[base_i + 12] = dw2.view(C, 4 * C, 1, 1)
@@ -142,11 +145,10 @@ class _ImageGPTStack(torch.autograd.Function):
             da2 = ops.linear_dgrad(du, blk["w1"])
             del du
             # h receives: LN2 path + direct (x_new = ... + h)
-            dh, dh_b, grads[base_i + 8], grads[base_i + 9] = ops.layernorm_bwd(
-                da2, blk["h"], ln2_w.detach(), blk["mean2"], blk["rstd2"], dres0=dx)
+            dh, dh_b, grads[base_i + 8], grads[base_i + 9], grads[base_i + 7] = ops.layernorm_bwd(
+                da2, blk["h"], ln2_w.detach(), blk["mean2"], blk["rstd2"], dres0=dx, want_colsum=True)
             del da2
             # h = x + proj(attn)
-            grads[base_i + 7] = ops.bias_grad(dh)
             dwp = torch.zeros(C, H * dv_slot, dtype=F32, device=dev)
             ops.linear_wgrad(dh_b, blk["o"], dwp)
             grads[base_i + 6] = (dwp if meta["dv"] == dv_slot else dwp[:, blk["cols_v"]]).reshape(C, C, 1, 1)
@@ -168,17 +170,17 @@ class _ImageGPTStack(torch.autograd.Function):
             da1 = ops.linear_dgrad(dqkv, blk["wqkv"])
             del dqkv
             # x receives: LN1 path + direct from h (dh) + direct from x_new (dx)
-            dx, dx_b, grads[base_i + 0], grads[base_i + 1] = ops.layernorm_bwd(
-                da1, blk["xs"], ln1_w.detach(), blk["mean1"], blk["rstd1"], dres0=dx, dres1=dh)
+            dx, dx_b, grads[base_i + 0], grads[base_i + 1], dx_sum = ops.layernorm_bwd(
+                da1, blk["xs"], ln1_w.detach(), blk["mean1"], blk["rstd1"], dres0=dx, dres1=dh, want_colsum=True)
             del da1, dh, dh_b
             sv["blocks"][b] = None  # release this block's activations
 
         in_w = params[1]
         dw_in = torch.zeros_like(in_w)
-        db_in = torch.zeros(C, dtype=F32, device=dev)
+        db_in = dx_sum  # bias gradient of the input conv = column sums of the stream gradient
         dx_in = torch.empty(n, cin, h, w, dtype=F32, device=dev)
         L.conv_small_bwd(sv["x_in"], in_w.detach().contiguous(), dx, (in_w.shape[2] // 2, in_w.shape[3] // 2), dw=dw_in,
-                         dbias=db_in, dx=dx_in)
+                         dbias=None, dx=dx_in)
         grads[1], grads[2] = dw_in, db_in
         grads[0] = dx_in.sum(dim=0, keepdim=True)
         ctx.saved = None

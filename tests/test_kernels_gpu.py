@@ -217,7 +217,9 @@ def test_layernorm_fwd_bwd(L, P, C):
     dx_b = torch.empty(P, C, device=_dev(), dtype=torch.bfloat16)
     dgam = torch.zeros(C, device=_dev())
     dbet = torch.zeros(C, device=_dev())
-    L.layernorm_bwd(dy, x, gamma, mean, rstd, dres0=r0, dres1=r1, dx_f32=dx_f, dx_bf16=dx_b, dgamma=dgam, dbeta=dbet)
+    dxs = torch.zeros(C, device=_dev())
+    L.layernorm_bwd(dy, x, gamma, mean, rstd, dres0=r0, dres1=r1, dx_f32=dx_f, dx_bf16=dx_b, dgamma=dgam, dbeta=dbet,
+                    dx_colsum=dxs)
     # bf16 dy variant
     dx_f2 = torch.empty(P, C, device=_dev())
     L.layernorm_bwd(dy.bfloat16(), x, gamma, mean, rstd, dx_f32=dx_f2)
@@ -228,6 +230,7 @@ def test_layernorm_fwd_bwd(L, P, C):
     assert_close("ln dx bf16", dx_b, xr.grad + r0 + r1, rtol=2 ** -8)
     assert_close("ln dgamma", dgam, gr.grad, rtol=1e-4, atol=1e-3)
     assert_close("ln dbeta", dbet, br.grad, rtol=1e-4, atol=1e-3)
+    assert_close("ln colsum(dx)", dxs, (xr.grad + r0 + r1).sum(0), rtol=1e-4, atol=1e-3)
     xr2 = x.clone().requires_grad_(True)
     torch.nn.functional.layer_norm(xr2, (C,), gamma, beta, 1e-5).backward(dy.bfloat16().float())
     assert_close("ln dx (bf16 dy)", dx_f2, xr2.grad, rtol=1e-5, atol=1e-5)
