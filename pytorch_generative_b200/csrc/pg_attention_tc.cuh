@@ -361,13 +361,26 @@ attn_bwd_tc_kernel(const __grid_constant__ AttnTmaps tm, const AttnArgs a, const
     const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
     const float sl2 = a.scale * 1.4426950408889634f;
     const int k0 = j * AT;
+    // row statistics are fetched one iteration ahead so their global-load latency hides behind the MMAs
+    const size_t stat_base = ((size_t)n * a.H + h) * a.S;
+    float lse_next = 0.f, delta_next = 0.f;
+    if (j * AT + r < a.S) {
+      lse_next = a.lse_in[stat_base + j * AT + r];
+      delta_next = a.delta[stat_base + j * AT + r];
+    }
     for (int it = 0; it < niter; ++it) {
       const int i = j + it;
       const int qi = i * AT + r;
       const bool row_ok = qi < a.S;
-      const size_t stat = ((size_t)n * a.H + h) * a.S + qi;
-      const float lse2 = row_ok ? a.lse_in[stat] * 1.4426950408889634f : 0.f;
-      const float delta = row_ok ? a.delta[stat] : 0.f;
+      const float lse2 = lse_next * 1.4426950408889634f;
+      const float delta = delta_next;
+      if (it + 1 < niter && qi + AT < a.S) {
+        lse_next = a.lse_in[stat_base + qi + AT];
+        delta_next = a.delta[stat_base + qi + AT];
+      } else {
+        lse_next = 0.f;
+        delta_next = 0.f;
+      }
       const int qlim = row_ok ? qi - a.strict : -1;  // invalid rows see no keys
       const bool need_mask = (it == 0) || (i == T - 1);
       mbar_wait(s_full, it & 1);

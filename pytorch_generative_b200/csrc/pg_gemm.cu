@@ -188,13 +188,12 @@ __device__ __forceinline__ void slab_bf16_store(uint8_t* slab, int r, const floa
         make_uint4(pack_bf16x2(v[8 * u], v[8 * u + 1]), pack_bf16x2(v[8 * u + 2], v[8 * u + 3]),
                    pack_bf16x2(v[8 * u + 4], v[8 * u + 5]), pack_bf16x2(v[8 * u + 6], v[8 * u + 7]));
 }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------------
 // tcgen05 kernel
 // ------------------------------------------------------------------------------------------------
 template <int BN, bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ EpiMaps em, const GemmParams p) {
   constexpr int B_STAGE_BYTES = BN * BK * 2;
@@ -232,7 +231,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int i = 0; i < ACC_STAGES; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4);  // one arrive per epilogue warp
+      mbar_init(&tempty_bar[i], 8);  // one arrive per epilogue warp (2 groups x 4)
     }
     mbar_init(&in_full[0], 1);
     mbar_init(&in_full[1], 1);
@@ -321,36 +320,38 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue =====================
-    const int ew = warp - 4;  // == warp % 4 -> TMEM lanes [32*ew, 32*ew+32)
-    const int r = ew * 32 + lane;  // row inside the tile
+    // ===================== epilogue: two warpgroups, alternating 32-column chunks =====================
+    // Warp w may only touch TMEM lanes [32*(w%4), +32), so warps 4..7 (group 0) and 8..11 (group 1) cover the
+    // same 128 rows; group g owns every chunk whose position in this CTA's chunk sequence has parity g, its own
+    // staging stage, input barrier and named barrier.  Two groups double the issue slots of the epilogue math.
+    const int grp = (warp - 4) >> 2;
+    const int ew = warp & 3;        // TMEM lane quarter
+    const int r = ew * 32 + lane;   // row inside the tile
     const bool leader = (r == 0);
     const pg_gemm_epilogue& e = p.epi;
     constexpr int NCH = BN / 32;
     int as = 0;
     uint32_t aph = 0;
-    unsigned gc = 0;  // global chunk counter (staged path): stage = gc & 1
+    unsigned gc = 0;       // position of the next chunk in this CTA's chunk sequence (all tiles)
+    unsigned used = 0;     // chunks this group has processed (parity of in_full[grp])
+    uint8_t* const base = epi_smem + grp * p.epi_stage_bytes;
+    const uint32_t bar_id = 1 + grp;
 
-    auto issue_inputs = [&](int tile, int c, int st) {  // leader only
+    auto issue_inputs = [&](int tile, int c) {  // group leader only
       const int n_blk = tile % p.num_n_blk;
       const int m_blk = (tile / p.num_n_blk) % p.num_m_blk;
-      uint8_t* base = epi_smem + st * p.epi_stage_bytes;
       const int col0 = n_blk * BN + c * 32, row0 = m_blk * BM;
-      mbar_arrive_expect_tx(&in_full[st], p.in_bytes);
-      if (p.off_res0 >= 0) tma_load_2d(base + p.off_res0, &em.res0, &in_full[st], col0, row0);
-      if (p.off_res1 >= 0) tma_load_2d(base + p.off_res1, &em.res1, &in_full[st], col0, row0);
-      if (p.off_aux >= 0) tma_load_2d(base + p.off_aux, &em.aux, &in_full[st], col0, row0);
+      mbar_arrive_expect_tx(&in_full[grp], p.in_bytes);
+      if (p.off_res0 >= 0) tma_load_2d(base + p.off_res0, &em.res0, &in_full[grp], col0, row0);
+      if (p.off_res1 >= 0) tma_load_2d(base + p.off_res1, &em.res1, &in_full[grp], col0, row0);
+      if (p.off_aux >= 0) tma_load_2d(base + p.off_aux, &em.aux, &in_full[grp], col0, row0);
     };
-    // chunk `ahead` positions after chunk c of `tile` in this CTA's tile sequence -> TMA its inputs into stage st
-    auto prefetch_inputs = [&](int tile, int c, int ahead, int st) {
-      int idx = c + ahead, t = tile;
-      while (idx >= NCH) { idx -= NCH; t += gridDim.x; }
-      if (t < num_tiles) issue_inputs(t, idx, st);
+    // chunk at sequence position `pos` -> (tile, chunk)
+    auto prefetch_pos = [&](unsigned pos) {
+      const int t = blockIdx.x + (int)(pos / NCH) * (int)gridDim.x;
+      if (t < num_tiles) issue_inputs(t, (int)(pos % NCH));
     };
-    if (p.staged && p.in_bytes > 0 && leader) {
-      prefetch_inputs(blockIdx.x, 0, 0, 0);
-      prefetch_inputs(blockIdx.x, 0, 1, 1);
-    }
+    if (p.staged && p.in_bytes > 0 && leader) prefetch_pos(grp);
     __syncwarp();
 
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -361,85 +362,81 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_wait(&tfull_bar[as], aph);
       tc_fence_after();
       const int row = m_blk * BM + r;
-      if (!p.staged) {
 #pragma unroll 1
-        for (int c = 0; c < NCH; ++c) {
-          uint32_t acc[32];
-          tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * BN + c * 32, acc);
-          tmem_wait_ld();
-          const int col0 = n_blk * BN + c * 32;
+      for (int c = 0; c < NCH; ++c, ++gc) {
+        if ((gc & 1u) != (unsigned)grp) continue;  // the other group's chunk
+        const int col0 = n_blk * BN + c * 32;
+        uint32_t acc[32];
+        tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * BN + c * 32, acc);
+        tmem_wait_ld();
+        if (!p.staged) {
           if (row < p.M && col0 < p.N) epilogue_row32(p, row, col0, min(32, p.N - col0), ks == 0, acc);
+          continue;
         }
-      } else {
-#pragma unroll 1
-        for (int c = 0; c < NCH; ++c, ++gc) {
-          const int st = gc & 1;
-          uint8_t* base = epi_smem + st * p.epi_stage_bytes;
-          const int col0 = n_blk * BN + c * 32;
-          uint32_t acc[32];
-          tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * BN + c * 32, acc);
-          tmem_wait_ld();
-          float v[32];
+        float v[32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]) * e.alpha;
-          if (e.bias) {
-            if (col0 + 32 <= p.N) {
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]) * e.alpha;
+        if (e.bias) {
+          if (col0 + 32 <= p.N) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + col0) + i);
-                v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
-              }
-            } else {
-#pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (col0 + i < p.N) v[i] += __ldg(e.bias + col0 + i);
+            for (int i = 0; i < 8; ++i) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + col0) + i);
+              v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
             }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (col0 + i < p.N) v[i] += __ldg(e.bias + col0 + i);
           }
-          if (p.in_bytes > 0) mbar_wait(&in_full[st], (gc >> 1) & 1);
-          if (p.off_aux >= 0) {
-            float x[32];
-            slab_bf16_load(base + p.off_aux, r, x);
-            if (e.dact == PG_ACT_GELU) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] *= pg_act_bwd(PG_ACT_GELU, x[i]);
-            } else {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] *= pg_act_bwd(e.dact, x[i]);
-            }
-          }
-          if (p.off_res0 >= 0) slab_f32_add(base + p.off_res0, r, v);
-          if (p.off_res1 >= 0) slab_f32_add(base + p.off_res1, r, v);
-          // the TMA store that last read this stage's output slabs (2 chunks ago) must have drained them
-          if (leader) tma_store_wait_read<1>();
-          __syncwarp();  // bar.sync / tcgen05.ld are warp-aligned: reconverge after every leader-only section
-          epi_bar_sync();
-          if (p.off_outf >= 0) slab_f32_store(base + p.off_outf, r, v);
-          if (p.off_outp >= 0) slab_bf16_store(base + p.off_outp, r, v);
-          if (p.off_outb >= 0) {
-            if (e.act == PG_ACT_GELU) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = pg_act_fwd(PG_ACT_GELU, v[i]);
-            } else if (e.act == PG_ACT_RELU) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
-            } else if (e.act != PG_ACT_NONE) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = pg_act_fwd(e.act, v[i]);
-            }
-            slab_bf16_store(base + p.off_outb, r, v);
-          }
-          fence_proxy_async_smem();
-          epi_bar_sync();
-          if (leader) {
-            const int row0 = m_blk * BM;
-            if (p.off_outf >= 0) tma_store_2d(&em.out_f32, base + p.off_outf, col0, row0);
-            if (p.off_outp >= 0) tma_store_2d(&em.out_pre, base + p.off_outp, col0, row0);
-            if (p.off_outb >= 0) tma_store_2d(&em.out_bf16, base + p.off_outb, col0, row0);
-            tma_store_commit();
-            if (p.in_bytes > 0) prefetch_inputs(tile, c, 2, st);  // refill this stage with the chunk two ahead
-          }
-          __syncwarp();
         }
+        if (p.in_bytes > 0) mbar_wait(&in_full[grp], used & 1);
+        if (p.off_aux >= 0) {
+          float x[32];
+          slab_bf16_load(base + p.off_aux, r, x);
+          if (e.dact == PG_ACT_GELU) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] *= pg_act_bwd(PG_ACT_GELU, x[i]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] *= pg_act_bwd(e.dact, x[i]);
+          }
+        }
+        if (p.off_res0 >= 0) slab_f32_add(base + p.off_res0, r, v);
+        if (p.off_res1 >= 0) slab_f32_add(base + p.off_res1, r, v);
+        // this group's previous TMA store must have finished reading the output slabs
+        if (leader) tma_store_wait_read<0>();
+        __syncwarp();  // bar.sync / tcgen05.ld are warp-aligned: reconverge after every leader-only section
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+        if (p.off_outf >= 0) slab_f32_store(base + p.off_outf, r, v);
+        if (p.off_outp >= 0) slab_bf16_store(base + p.off_outp, r, v);
+        if (p.off_outb >= 0) {
+          if (e.act == PG_ACT_GELU) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = pg_act_fwd(PG_ACT_GELU, v[i]);
+          } else if (e.act == PG_ACT_RELU) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+          } else if (e.act != PG_ACT_NONE) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = pg_act_fwd(e.act, v[i]);
+          }
+          slab_bf16_store(base + p.off_outb, r, v);
+        }
+        fence_proxy_async_smem();
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+        if (leader) {
+          const int row0 = m_blk * BM;
+          if (p.off_outf >= 0) {
+            if (e.accumulate) tma_reduce_add_2d(&em.out_f32, base + p.off_outf, col0, row0);
+            else tma_store_2d(&em.out_f32, base + p.off_outf, col0, row0);
+          }
+          if (p.off_outp >= 0) tma_store_2d(&em.out_pre, base + p.off_outp, col0, row0);
+          if (p.off_outb >= 0) tma_store_2d(&em.out_bf16, base + p.off_outb, col0, row0);
+          tma_store_commit();
+          if (p.in_bytes > 0) prefetch_pos(gc + 2);  // this group's next chunk
+        }
+        ++used;
+        __syncwarp();
       }
       tc_fence_before();
       __syncwarp();
@@ -506,7 +503,9 @@ int launch_tc(const void* A, int64_t lda, const void* B, int64_t ldb, GemmParams
   p.off_res0 = p.off_res1 = p.off_aux = p.off_outf = p.off_outb = p.off_outp = -1;
   p.in_bytes = 0;
   p.epi_stage_bytes = 0;
-  p.staged = (p.vec_ok && !e.accumulate && p.splits == 1) ? 1 : 0;
+  const bool pure_acc = e.accumulate && !e.bias && !e.res0 && !e.res1 && e.dact == PG_ACT_NONE && !e.out_bf16 &&
+                        !e.out_pre && e.alpha == 1.0f;  // split-K / grad accumulation: TMA reduce-add of the raw tile
+  p.staged = (p.vec_ok && (pure_acc || (!e.accumulate && p.splits == 1))) ? 1 : 0;
   if (p.staged) {
     int off = 0;
     auto add = [&](int& slot, int bytes) { slot = off; off += bytes; };
@@ -535,7 +534,7 @@ int launch_tc(const void* A, int64_t lda, const void* B, int64_t ldb, GemmParams
   PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
   const int num_tiles = p.num_m_blk * p.num_n_blk * p.splits;
   const int grid = min(num_tiles, pg_num_sms());
-  kern<<<grid, 256, smem_bytes, stream>>>(tmA, tmB, em, p);
+  kern<<<grid, 384, smem_bytes, stream>>>(tmA, tmB, em, p);
   return pg_check_launch("pg_gemm_bf16(tcgen05)");
 }
 
@@ -554,7 +553,7 @@ int dispatch_bn(const void* A, int64_t lda, const void* B, int64_t ldb, GemmPara
     // next to a >= 3-deep operand pipeline; those GEMMs are HBM-bound anyway, so take the 128-wide tile.
     const int epi = (e.res0 ? SLAB_F32 : 0) + (e.res1 ? SLAB_F32 : 0) + (e.dact != PG_ACT_NONE ? SLAB_BF16 : 0) +
                     (e.out_f32 ? SLAB_F32 : 0) + (e.out_pre ? SLAB_BF16 : 0) + (e.out_bf16 ? SLAB_BF16 : 0);
-    const bool staged = p.vec_ok && !e.accumulate && p.splits == 1;
+    const bool staged = p.vec_ok && (!e.accumulate || (!e.bias && !e.res0 && !e.res1)) ;
     if (staged && (SMEM_LIMIT - 2 * epi - 1536) / (A_STAGE_BYTES + 256 * BK * 2) < 4) bn = 128;
     // Narrow problems with few tiles prefer 128 to spread over more SMs.
     if (bn == 256 && ((p.M + BM - 1) / BM) * ((p.N + 255) / 256) * p.splits < pg_num_sms() && p.N % 256 != 0) bn = 128;

@@ -77,10 +77,11 @@ class _ImageGPTStack(torch.autograd.Function):
             qkv, _, _ = ops.linear_fwd(a1, wqkv, bqkv)
             q, k, v = qkv[:, : H * slot], qkv[:, H * slot: 2 * H * slot], qkv[:, 2 * H * slot:]
             o, lse = ops.attn_fwd(q, k, v, n, S, H, meta["dk"], dv_slot, False)
-            cols_v = meta["rows_v"] - H * slot
-            if meta["dv"] == dv_slot:
+            cols_v = None
+            if meta["identity"]:
                 wp = ops.pack_weight(p_w)
             else:
+                cols_v = meta["rows_v"] - H * slot
                 wp32 = torch.zeros(C, H * dv_slot, dtype=F32, device=x.device)
                 wp32[:, cols_v] = p_w.detach().reshape(C, -1)
                 wp = ops.to_bf16(wp32)
@@ -151,7 +152,7 @@ class _ImageGPTStack(torch.autograd.Function):
             # h = x + proj(attn)
             dwp = torch.zeros(C, H * dv_slot, dtype=F32, device=dev)
             ops.linear_wgrad(dh_b, blk["o"], dwp)
-            grads[base_i + 6] = (dwp if meta["dv"] == dv_slot else dwp[:, blk["cols_v"]]).reshape(C, C, 1, 1)
+            grads[base_i + 6] = (dwp if meta["identity"] else dwp[:, blk["cols_v"]]).reshape(C, C, 1, 1)
             do = ops.linear_dgrad(dh_b, blk["wp"])
             qkv = blk["qkv"]
             q, k, v = qkv[:, : H * slot], qkv[:, H * slot: 2 * H * slot], qkv[:, 2 * H * slot:]
@@ -162,11 +163,17 @@ class _ImageGPTStack(torch.autograd.Function):
             dbqkv = ops.bias_grad(dqkv)
             dwqkv = torch.zeros(blk["wqkv"].shape, dtype=F32, device=dev)
             ops.linear_wgrad(dqkv, blk["a1"], dwqkv)
-            rq, rv = meta["rows_q"], meta["rows_v"]
-            grads[base_i + 2] = dwqkv[rq].reshape(C, C, 1, 1)
-            grads[base_i + 3] = dbqkv[rq]
-            grads[base_i + 4] = torch.cat((dwqkv[rq + H * slot], dwqkv[rv + H * slot])).reshape(2 * C, C, 1, 1)
-            grads[base_i + 5] = torch.cat((dbqkv[rq + H * slot], dbqkv[rv + H * slot]))
+            if meta["identity"]:  # heads fill their slots: plain slices of the fused gradient buffers
+                grads[base_i + 2] = dwqkv[:C].view(C, C, 1, 1)
+                grads[base_i + 3] = dbqkv[:C]
+                grads[base_i + 4] = dwqkv[C:].view(2 * C, C, 1, 1)
+                grads[base_i + 5] = dbqkv[C:]
+            else:
+                rq, rv = meta["rows_q"], meta["rows_v"]
+                grads[base_i + 2] = dwqkv[rq].reshape(C, C, 1, 1)
+                grads[base_i + 3] = dbqkv[rq]
+                grads[base_i + 4] = torch.cat((dwqkv[rq + H * slot], dwqkv[rv + H * slot])).reshape(2 * C, C, 1, 1)
+                grads[base_i + 5] = torch.cat((dbqkv[rq + H * slot], dbqkv[rv + H * slot]))
             da1 = ops.linear_dgrad(dqkv, blk["wqkv"])
             del dqkv
             # x receives: LN1 path + direct from h (dh) + direct from x_new (dx)

@@ -208,9 +208,7 @@ def pack_qkv_weights(q_w, q_b, kv_w, kv_b, n_heads, embed, out_ch, cin_q_pad, ci
     dev = q_w.device
     if dk == ops.HEAD_SLOT and dv == dv_slot and q_w[0].numel() == cin_q_pad and kv_w[0].numel() == cin_kv_pad:
         # heads already fill their slots (e.g. ImageGPT 512ch / 8 heads): no scatter, just cast
-        rows_q = torch.arange(n_heads * dk, device=dev)
-        rows_v = torch.arange(n_heads * dv, device=dev) + n_heads * dk
-        meta = dict(dk=dk, dv=dv, dv_slot=dv_slot, rows_q=rows_q, rows_v=rows_v)
+        meta = dict(dk=dk, dv=dv, dv_slot=dv_slot, rows_q=None, rows_v=None, identity=True)
         return (ops.to_bf16(q_w.detach().reshape(embed, -1)), q_b.detach(),
                 ops.to_bf16(kv_w.detach().reshape(embed + out_ch, -1)), kv_b.detach(), meta)
     rows_q = head_slot_rows(n_heads, dk, ops.HEAD_SLOT).to(dev)
@@ -226,7 +224,7 @@ def pack_qkv_weights(q_w, q_b, kv_w, kv_b, n_heads, embed, out_ch, cin_q_pad, ci
     bkv = torch.zeros(n_heads * (ops.HEAD_SLOT + dv_slot), dtype=F32, device=dev)
     bkv[rows_q] = kv_b.detach()[:embed]
     bkv[rows_v] = kv_b.detach()[embed:]
-    meta = dict(dk=dk, dv=dv, dv_slot=dv_slot, rows_q=rows_q, rows_v=rows_v)
+    meta = dict(dk=dk, dv=dv, dv_slot=dv_slot, rows_q=rows_q, rows_v=rows_v, identity=False)
     return ops.to_bf16(wq), bq, ops.to_bf16(wkv), bkv, meta
 
 
@@ -253,10 +251,14 @@ class _AttentionFn(torch.autograd.Function):
         k, v = kv[:, : H * ops.HEAD_SLOT], kv[:, H * ops.HEAD_SLOT:]
         o, lse = ops.attn_fwd(q, k, v, n, S, H, meta["dk"], dv_slot, strict)
         # output projection reads the slot-padded o through a column-scattered weight
-        wp = torch.zeros(out_ch, H * dv_slot, dtype=F32, device=x.device)
-        cols_v = meta["rows_v"] - H * ops.HEAD_SLOT
-        wp[:, cols_v] = p_w.detach().reshape(out_ch, -1)
-        wp = ops.to_bf16(wp)
+        if meta["identity"]:
+            cols_v = None
+            wp = ops.pack_weight(p_w)
+        else:
+            wp = torch.zeros(out_ch, H * dv_slot, dtype=F32, device=x.device)
+            cols_v = meta["rows_v"] - H * ops.HEAD_SLOT
+            wp[:, cols_v] = p_w.detach().reshape(out_ch, -1)
+            wp = ops.to_bf16(wp)
         _, _, y_pm = ops.linear_fwd(o, wp, p_b.detach(), want_bf16=False, want_f32=True)
         ctx.save_for_backward(a_kv, q, kv, o, lse, wq, wkv, wp)
         ctx.meta = dict(meta, n=n, h=h, w=w, cin=cin, ce=ce, cin_p=cin_p, H=H, embed=embed, out_ch=out_ch, strict=strict,
@@ -294,6 +296,11 @@ class _AttentionFn(torch.autograd.Function):
         cin, ce, embed = m["cin"], m["ce"], m["embed"]
         dx = ops.pm_to_nchw(da_kv[:, :cin].contiguous(), n, cin, h, w)
         dextra = ops.pm_to_nchw(da_kv[:, cin:cin + ce].contiguous(), n, ce, h, w) if ce else None
+        if m["identity"]:
+            g_qw = dwq[:, :cin].reshape(embed, cin, 1, 1)
+            g_kvw = dwkv[:, : cin + ce].reshape(embed + m["out_ch"], cin + ce, 1, 1)
+            g_pw = dwp[: m["out_ch"]].reshape(m["out_ch"], m["out_ch"], 1, 1)
+            return (dx, dextra, g_qw, dbq, g_kvw, dbkv, g_pw, dp_b, None, None, None, None)
         rq, rv = m["rows_q"], m["rows_v"]
         g_qw = dwq[rq, :cin].reshape(embed, cin, 1, 1)
         g_kvw = torch.cat((dwkv[rq, : cin + ce], dwkv[rv, : cin + ce])).reshape(embed + m["out_ch"], cin + ce, 1, 1)
