@@ -43,6 +43,7 @@ struct GemmParams {
   int vec_ok;       // all epilogue pointers/pitches allow 16-byte vector access (direct path)
   // staged (TMA) epilogue plan
   int staged;
+  int epi_depth;    // staging stages per epilogue warpgroup (1 or 2)
   int epi_stage_bytes;
   int off_res0, off_res1, off_aux, off_outf, off_outb, off_outp;  // slab offsets inside an epilogue stage, -1 = absent
   int in_bytes;  // bytes TMA-loaded per chunk (res0 + res1 + aux slabs)
@@ -210,12 +211,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int STAGES = p.stages;
   uint8_t* epi_smem = smem + STAGES * STAGE_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_smem + 2 * p.epi_stage_bytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_smem + 2 * p.epi_depth * p.epi_stage_bytes);
   uint64_t* empty_bar = full_bar + MAX_STAGES;
   uint64_t* tfull_bar = empty_bar + MAX_STAGES;
   uint64_t* tempty_bar = tfull_bar + ACC_STAGES;
-  uint64_t* in_full = tempty_bar + ACC_STAGES;  // [2] epilogue input slabs landed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(in_full + 2);
+  uint64_t* in_full = tempty_bar + ACC_STAGES;  // [2 groups][2 stages] epilogue input slabs landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(in_full + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -233,8 +234,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], 8);  // one arrive per epilogue warp (2 groups x 4)
     }
-    mbar_init(&in_full[0], 1);
-    mbar_init(&in_full[1], 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&in_full[i], 1);
     fence_barrier_init();
     fence_proxy_async_smem();
   }
@@ -334,24 +334,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t aph = 0;
     unsigned gc = 0;       // position of the next chunk in this CTA's chunk sequence (all tiles)
     unsigned used = 0;     // chunks this group has processed (parity of in_full[grp])
-    uint8_t* const base = epi_smem + grp * p.epi_stage_bytes;
+    const int depth = p.epi_depth;  // staging stages owned by this group
+    uint8_t* const grp_base = epi_smem + grp * depth * p.epi_stage_bytes;
     const uint32_t bar_id = 1 + grp;
 
-    auto issue_inputs = [&](int tile, int c) {  // group leader only
+    auto issue_inputs = [&](int tile, int c, int st) {  // group leader only
       const int n_blk = tile % p.num_n_blk;
       const int m_blk = (tile / p.num_n_blk) % p.num_m_blk;
       const int col0 = n_blk * BN + c * 32, row0 = m_blk * BM;
-      mbar_arrive_expect_tx(&in_full[grp], p.in_bytes);
-      if (p.off_res0 >= 0) tma_load_2d(base + p.off_res0, &em.res0, &in_full[grp], col0, row0);
-      if (p.off_res1 >= 0) tma_load_2d(base + p.off_res1, &em.res1, &in_full[grp], col0, row0);
-      if (p.off_aux >= 0) tma_load_2d(base + p.off_aux, &em.aux, &in_full[grp], col0, row0);
+      uint8_t* b = grp_base + st * p.epi_stage_bytes;
+      uint64_t* bar = &in_full[grp * 2 + st];
+      mbar_arrive_expect_tx(bar, p.in_bytes);
+      if (p.off_res0 >= 0) tma_load_2d(b + p.off_res0, &em.res0, bar, col0, row0);
+      if (p.off_res1 >= 0) tma_load_2d(b + p.off_res1, &em.res1, bar, col0, row0);
+      if (p.off_aux >= 0) tma_load_2d(b + p.off_aux, &em.aux, bar, col0, row0);
     };
     // chunk at sequence position `pos` -> (tile, chunk)
-    auto prefetch_pos = [&](unsigned pos) {
+    auto prefetch_pos = [&](unsigned pos, int st) {
       const int t = blockIdx.x + (int)(pos / NCH) * (int)gridDim.x;
-      if (t < num_tiles) issue_inputs(t, (int)(pos % NCH));
+      if (t < num_tiles) issue_inputs(t, (int)(pos % NCH), st);
     };
-    if (p.staged && p.in_bytes > 0 && leader) prefetch_pos(grp);
+    if (p.staged && p.in_bytes > 0 && leader) {
+      prefetch_pos(grp, 0);
+      if (depth > 1) prefetch_pos(grp + 2, 1);
+    }
     __syncwarp();
 
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -389,7 +395,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               if (col0 + i < p.N) v[i] += __ldg(e.bias + col0 + i);
           }
         }
-        if (p.in_bytes > 0) mbar_wait(&in_full[grp], used & 1);
+        const int st = (depth > 1) ? (int)(used & 1u) : 0;
+        uint8_t* const base = grp_base + st * p.epi_stage_bytes;
+        if (p.in_bytes > 0) mbar_wait(&in_full[grp * 2 + st], (depth > 1 ? (used >> 1) : used) & 1u);
         if (p.off_aux >= 0) {
           float x[32];
           slab_bf16_load(base + p.off_aux, r, x);
@@ -403,8 +411,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         if (p.off_res0 >= 0) slab_f32_add(base + p.off_res0, r, v);
         if (p.off_res1 >= 0) slab_f32_add(base + p.off_res1, r, v);
-        // this group's previous TMA store must have finished reading the output slabs
-        if (leader) tma_store_wait_read<0>();
+        // the TMA store that last used this stage's output slabs must have finished reading them
+        if (leader) {
+          if (depth > 1) tma_store_wait_read<1>();
+          else tma_store_wait_read<0>();
+        }
         __syncwarp();  // bar.sync / tcgen05.ld are warp-aligned: reconverge after every leader-only section
         asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
         if (p.off_outf >= 0) slab_f32_store(base + p.off_outf, r, v);
@@ -433,7 +444,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (p.off_outp >= 0) tma_store_2d(&em.out_pre, base + p.off_outp, col0, row0);
           if (p.off_outb >= 0) tma_store_2d(&em.out_bf16, base + p.off_outb, col0, row0);
           tma_store_commit();
-          if (p.in_bytes > 0) prefetch_pos(gc + 2);  // this group's next chunk
+          if (p.in_bytes > 0) prefetch_pos(gc + 2 * depth, st);  // refill this stage for this group's chunk `depth` ahead
         }
         ++used;
         __syncwarp();
@@ -523,7 +534,11 @@ int launch_tc(const void* A, int64_t lda, const void* B, int64_t ldb, GemmParams
     if (e.out_pre && pg_make_tmap_2d(&em.out_pre, e.out_pre, 2, p.M, p.N, e.ld_out_pre, BM, 32, 64)) return 1;
     if (e.out_bf16 && pg_make_tmap_2d(&em.out_bf16, e.out_bf16, 2, p.M, p.N, e.ld_out_bf16, BM, 32, 64)) return 1;
   }
-  const int fixed = 2 * p.epi_stage_bytes + 1024 /*align slack*/ + 512 /*barriers*/;
+  // two staging stages per epilogue group when that still leaves a >= 3-deep operand pipeline
+  // (short-K tiles only: there the epilogue is a large share of the tile time; long-K tiles want the smem for
+  // a deeper operand pipeline instead)
+  p.epi_depth = (p.staged && p.k_per_split <= 16 && (SMEM_LIMIT - 4 * p.epi_stage_bytes - 1536) / STAGE_BYTES >= 3) ? 2 : 1;
+  const int fixed = 2 * p.epi_depth * p.epi_stage_bytes + 1024 /*align slack*/ + 512 /*barriers*/;
   int stages = (SMEM_LIMIT - fixed) / STAGE_BYTES;
   if (stages > 8) stages = 8;
   if (stages > p.k_iters + 1) stages = p.k_iters + 1 > 2 ? p.k_iters + 1 : 2;
@@ -554,7 +569,7 @@ int dispatch_bn(const void* A, int64_t lda, const void* B, int64_t ldb, GemmPara
     const int epi = (e.res0 ? SLAB_F32 : 0) + (e.res1 ? SLAB_F32 : 0) + (e.dact != PG_ACT_NONE ? SLAB_BF16 : 0) +
                     (e.out_f32 ? SLAB_F32 : 0) + (e.out_pre ? SLAB_BF16 : 0) + (e.out_bf16 ? SLAB_BF16 : 0);
     const bool staged = p.vec_ok && (!e.accumulate || (!e.bias && !e.res0 && !e.res1)) ;
-    if (staged && (SMEM_LIMIT - 2 * epi - 1536) / (A_STAGE_BYTES + 256 * BK * 2) < 4) bn = 128;
+    if (staged && (SMEM_LIMIT - 2 * epi - 1536) / (A_STAGE_BYTES + 256 * BK * 2) < 3) bn = 128;
     // Narrow problems with few tiles prefer 128 to spread over more SMs.
     if (bn == 256 && ((p.M + BM - 1) / BM) * ((p.N + 255) / 256) * p.splits < pg_num_sms() && p.N % 256 != 0) bn = 128;
   }
