@@ -120,8 +120,12 @@ int pg_bce_logits_fwd_bwd(const float* logits, const float* target, int64_t nume
 /* Layout converters for the Module boundary (NCHW fp32 <-> pixel-major). */
 int pg_nchw_to_pm(const float* x_nchw, int N, int C, int HW, void* out, int out_is_f32, int64_t ld_out,
                   void* stream);
-int pg_pm_to_nchw(const void* x_pm, int x_is_f32, int64_t ld_x, int N, int C, int HW, float* out_nchw,
+/* act (PG_ACT_*) is applied on the way out: used for activations that follow a convolution. */
+int pg_pm_to_nchw(const void* x_pm, int x_is_f32, int64_t ld_x, int N, int C, int HW, int act, float* out_nchw,
                   void* stream);
+/* out = bf16(dy * act'(pre)): gradient through such an output activation. */
+int pg_dact_mul(const void* dy_bf16, int64_t ld_dy, const float* pre_f32, int64_t ld_pre, int P, int C, int act,
+                void* out_bf16, int64_t ld_out, void* stream);
 /* fp32 -> bf16 cast of a dense buffer (weights packing; masked taps already zeroed by the caller). */
 int pg_cast_f32_to_bf16(const float* x, void* y, int64_t numel, void* stream);
 
@@ -155,12 +159,26 @@ int pg_causal_attn_bwd(const void* q, int64_t ld_q, const void* k, int64_t ld_k,
  * wgrad is dense over kh*kw (masked taps receive gradient, as autograd does in the reference).
  * ------------------------------------------------------------------------------------------- */
 int pg_conv_small_fwd(const float* x_nchw, const float* w_oihw, const float* bias, int N, int Cin, int H, int W,
-                      int Cout, int kh, int kw, int pad_h, int pad_w, float* out_f32, void* out_bf16,
-                      int act_bf16, void* stream);
+                      int Cout, int kh, int kw, int pad_h, int pad_w, int pre_act /* applied to x */, float* out_f32,
+                      void* out_bf16, int act_bf16, void* stream);
 int pg_conv_small_bwd(const float* x_nchw, const float* w_oihw, const float* dy_pm /* [P,Cout] fp32 */, int N,
-                      int Cin, int H, int W, int Cout, int kh, int kw, int pad_h, int pad_w,
+                      int Cin, int H, int W, int Cout, int kh, int kw, int pad_h, int pad_w, int pre_act,
                       float* dw_oihw /* accumulated */, float* dbias /* accumulated */,
                       float* dx_nchw /* or NULL; overwritten */, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Wide-channel tap-list convolutions (CausalConv2d with Cin >= 8; GatedPixelCNN 1xN / Nx1 — reference
+ * gated_pixel_cnn.py:63-99 with the crops at 115,121; PixelSNAIL 2x2 — pixel_snail.py:41-56).
+ * conv(x)[p] = sum_t W_t . x[p + (dy_t, dx_t)], zero outside the image (= the reference's pad + front crop).
+ * pg_tap_gather builds X_cat[p, t*C + c] = act(x[p + off_t, c]) in bf16; the contraction over K = T*C is
+ * pg_gemm_bf16 (forward, dgrad to dX_cat, wgrad from X_cat); pg_tap_scatter folds dX_cat back:
+ * dx[p, c] = act'(x_pre[p, c]) * sum_t dX_cat[p - off_t, t*C + c].  C % 8 == 0, T <= 32.
+ * ------------------------------------------------------------------------------------------- */
+int pg_tap_gather(const void* x_pm, int64_t ld_x, int N, int H, int W, int C, int T, const int* dy /* host */,
+                  const int* dx /* host */, int act, void* out /* bf16 [P, T*C] */, void* stream);
+int pg_tap_scatter(const void* dxcat /* bf16 [P, T*C] */, int N, int H, int W, int C, int T, const int* dy,
+                   const int* dx, int act, const void* x_pre /* bf16 [P, ld_pre] or NULL */, int64_t ld_pre,
+                   float* dx_f32, void* dx_bf16, int64_t ld_dx, void* stream);
 
 #ifdef __cplusplus
 }

@@ -44,13 +44,16 @@ _SIGNATURES = {
     "pg_gated_act_bwd": [_vp, _i32, _vp, _i32, _i32, _i32, _i32, _vp, _i32, _vp],
     "pg_bce_logits_fwd_bwd": [_vp, _vp, _i64, _f32, _vp, _vp, _vp],
     "pg_nchw_to_pm": [_vp, _i32, _i32, _i32, _vp, _i32, _i64, _vp],
-    "pg_pm_to_nchw": [_vp, _i32, _i64, _i32, _i32, _i32, _vp, _vp],
+    "pg_pm_to_nchw": [_vp, _i32, _i64, _i32, _i32, _i32, _i32, _vp, _vp],
+    "pg_dact_mul": [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _vp, _i64, _vp],
     "pg_cast_f32_to_bf16": [_vp, _vp, _i64, _vp],
     "pg_causal_attn_fwd": [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _i32, _i32, _vp],
     "pg_causal_attn_bwd": [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _i64,
                            _vp, _i64, _i32, _i32, _i32, _i32, _i32, _f32, _i32, _i32, _vp],
-    "pg_conv_small_fwd": [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp],
-    "pg_conv_small_bwd": [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp],
+    "pg_conv_small_fwd": [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp],
+    "pg_conv_small_bwd": [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp],
+    "pg_tap_gather": [_vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _vp],
+    "pg_tap_scatter": [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _i64, _vp, _vp, _i64, _vp],
 }
 EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + ["pg_abi_version", "pg_last_error", "pg_sm_count", "pg_launch_count"])
 
@@ -240,13 +243,22 @@ def nchw_to_pm(x, out):
     _check(lib.pg_nchw_to_pm(_ptr(x), N, C, H * W, p, int(out.dtype == torch.float32), ld, _stream()), "pg_nchw_to_pm")
 
 
-def pm_to_nchw(x_pm, out):
+def pm_to_nchw(x_pm, out, act=ACT_NONE):
     lib = load()
     N, C, H, W = out.shape
     assert out.dtype == torch.float32 and out.is_contiguous()
     p, ld = _pm(x_pm)
-    _check(lib.pg_pm_to_nchw(p, int(x_pm.dtype == torch.float32), ld, N, C, H * W, _ptr(out), _stream()),
+    _check(lib.pg_pm_to_nchw(p, int(x_pm.dtype == torch.float32), ld, N, C, H * W, act, _ptr(out), _stream()),
            "pg_pm_to_nchw")
+
+
+def dact_mul(dy, pre, act, out):
+    """out = bf16(dy * act'(pre)); dy/out bf16 [P, C] views, pre fp32."""
+    lib = load()
+    (dp, ldd), (pp, ldp), (op, ldo) = _pm(dy), _pm(pre), _pm(out)
+    P, C = dy.shape
+    assert dy.dtype == torch.bfloat16 and pre.dtype == torch.float32 and out.dtype == torch.bfloat16
+    _check(lib.pg_dact_mul(dp, ldd, pp, ldp, P, C, act, op, ldo, _stream()), "pg_dact_mul")
 
 
 def cast_bf16(x, y):
@@ -277,19 +289,48 @@ def causal_attn_bwd(q, k, v, o, do, lse, delta, dq_accum, dq, dk_, dv_, N, S, H,
                                   impl, _stream()), "pg_causal_attn_bwd")
 
 
-def conv_small_fwd(x, w, bias, pad, out_f32=None, out_bf16=None, act_bf16=ACT_NONE):
+def conv_small_fwd(x, w, bias, pad, out_f32=None, out_bf16=None, act_bf16=ACT_NONE, pre_act=ACT_NONE):
     lib = load()
     N, Cin, H, W = x.shape
     Cout, _, kh, kw = w.shape
     assert x.is_contiguous() and w.is_contiguous() and x.dtype == torch.float32 and w.dtype == torch.float32
-    _check(lib.pg_conv_small_fwd(_ptr(x), _ptr(w), _ptr(bias), N, Cin, H, W, Cout, kh, kw, pad[0], pad[1],
+    _check(lib.pg_conv_small_fwd(_ptr(x), _ptr(w), _ptr(bias), N, Cin, H, W, Cout, kh, kw, pad[0], pad[1], pre_act,
                                  _ptr(out_f32), _ptr(out_bf16), act_bf16, _stream()), "pg_conv_small_fwd")
 
 
-def conv_small_bwd(x, w, dy_pm, pad, dw=None, dbias=None, dx=None):
+def conv_small_bwd(x, w, dy_pm, pad, dw=None, dbias=None, dx=None, pre_act=ACT_NONE):
     lib = load()
     N, Cin, H, W = x.shape
     Cout, _, kh, kw = w.shape
     assert dy_pm.dtype == torch.float32 and dy_pm.is_contiguous()
-    _check(lib.pg_conv_small_bwd(_ptr(x), _ptr(w), _ptr(dy_pm), N, Cin, H, W, Cout, kh, kw, pad[0], pad[1], _ptr(dw),
-                                 _ptr(dbias), _ptr(dx), _stream()), "pg_conv_small_bwd")
+    _check(lib.pg_conv_small_bwd(_ptr(x), _ptr(w), _ptr(dy_pm), N, Cin, H, W, Cout, kh, kw, pad[0], pad[1], pre_act,
+                                 _ptr(dw), _ptr(dbias), _ptr(dx), _stream()), "pg_conv_small_bwd")
+
+
+def _int_array(vals):
+    arr = (ctypes.c_int * len(vals))(*[int(v) for v in vals])
+    return arr
+
+
+def tap_gather(x_pm, N, H, W, C, taps, act, out):
+    """x_pm: [P, >=C] bf16; taps: list of (dy, dx); out: [P, T*C] bf16 contiguous."""
+    lib = load()
+    p, ld = _pm(x_pm)
+    dy, dx = _int_array([t[0] for t in taps]), _int_array([t[1] for t in taps])
+    assert out.is_contiguous() and out.dtype == torch.bfloat16 and x_pm.dtype == torch.bfloat16
+    _check(lib.pg_tap_gather(p, ld, N, H, W, C, len(taps), ctypes.cast(dy, ctypes.c_void_p), ctypes.cast(dx, ctypes.c_void_p),
+                             act, _ptr(out), _stream()), "pg_tap_gather")
+
+
+def tap_scatter(dxcat, N, H, W, C, taps, act, x_pre, dx_f32=None, dx_bf16=None):
+    lib = load()
+    assert dxcat.is_contiguous() and dxcat.dtype == torch.bfloat16
+    dy, dx = _int_array([t[0] for t in taps]), _int_array([t[1] for t in taps])
+    pre_p, pre_ld = (None, 0) if x_pre is None else _pm(x_pre)
+    tgt = dx_f32 if dx_f32 is not None else dx_bf16
+    _, ld_dx = _pm(tgt)
+    if dx_f32 is not None and dx_bf16 is not None:
+        assert dx_bf16.stride(0) == ld_dx
+    _check(lib.pg_tap_scatter(_ptr(dxcat), N, H, W, C, len(taps), ctypes.cast(dy, ctypes.c_void_p),
+                              ctypes.cast(dx, ctypes.c_void_p), act, pre_p, pre_ld, _ptr(dx_f32), _ptr(dx_bf16), ld_dx,
+                              _stream()), "pg_tap_scatter")

@@ -15,6 +15,7 @@ constexpr int MAX_K = 160;  // Cin*kh*kw upper bound (3*7*7 = 147)
 
 struct ConvArgs {
   int N, Cin, H, W, Cout, kh, kw, ph, pw, K;
+  int pre_act;  // activation applied to the input before the convolution (act(0) = 0, so it commutes with padding)
 };
 
 // Gathers the K-vector of input values under the kernel window of pixel p (zero padding).
@@ -24,7 +25,7 @@ __device__ __forceinline__ float patch_value(const float* __restrict__ x, const 
   const int i = r / a.kw, j = r % a.kw;
   const int yy = y + i - a.ph, xc = xx + j - a.pw;
   if (yy < 0 || yy >= a.H || xc < 0 || xc >= a.W) return 0.f;
-  return x[(((size_t)n * a.Cin + ci) * a.H + yy) * a.W + xc];
+  return pg_act_fwd(a.pre_act, x[(((size_t)n * a.Cin + ci) * a.H + yy) * a.W + xc]);
 }
 
 __global__ void __launch_bounds__(256)
@@ -125,7 +126,7 @@ conv_small_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ d
 // One warp per input pixel, lanes over output channels.
 __global__ void __launch_bounds__(256)
 conv_small_dgrad_kernel(const float* __restrict__ w, const float* __restrict__ dy, const ConvArgs a,
-                        float* __restrict__ dx) {
+                        const float* __restrict__ x, float* __restrict__ dx) {
   const int lane = threadIdx.x & 31;
   const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int HW = a.H * a.W;
@@ -147,18 +148,124 @@ conv_small_dgrad_kernel(const float* __restrict__ w, const float* __restrict__ d
       }
     }
     acc = warp_sum(acc);
-    if (lane == 0) dx[(((size_t)n * a.Cin + ci) * a.H + y) * a.W + xx] = acc;
+    if (lane == 0) {
+      const size_t off = (((size_t)n * a.Cin + ci) * a.H + y) * a.W + xx;
+      dx[off] = a.pre_act == PG_ACT_NONE ? acc : acc * pg_act_bwd(a.pre_act, x[off]);
+    }
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Tap gather / scatter for wide-channel convolutions (CausalConv2d with Cin >= 8, the GatedPixelCNN 1xN / Nx1 and
+// PixelSNAIL 2x2 convs: reference gated_pixel_cnn.py:63-99,115,121, pixel_snail.py:41-56, nn/convolution.py:41-43).
+// conv(x)[p] = sum_t W_t . x[p + (dy_t, dx_t)] with zero fill outside the image (the reference's pad + crop, SURVEY
+// Appendix A).  The contraction itself runs on the tcgen05 GEMM: gather builds X_cat[p, t*C + c] = act(x[p+off_t, c])
+// once (bf16, 16-byte chunks), the GEMM contracts over K = T*C, and backward scatters dX_cat back with the mirrored
+// offsets.  act(0) = 0 for every activation on the path (ReLU / ELU), so it commutes with the zero padding.
+// ------------------------------------------------------------------------------------------------
+struct TapArgs {
+  int N, H, W, C, T;
+  int dy[32], dx[32];
+};
+
+__global__ void __launch_bounds__(256)
+tap_gather_kernel(const bf16* __restrict__ x, int64_t ld_x, const TapArgs a, int act, bf16* __restrict__ out) {
+  const int c8n = a.C / 8;
+  const long long P = (long long)a.N * a.H * a.W;
+  const long long total = P * a.T * c8n;
+  const int HW = a.H * a.W;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(idx % c8n);
+    const int t = (int)((idx / c8n) % a.T);
+    const long long p = idx / ((long long)c8n * a.T);
+    const int n = (int)(p / HW), rem = (int)(p % HW);
+    const int ys = rem / a.W + a.dy[t], xs = rem % a.W + a.dx[t];
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (ys >= 0 && ys < a.H && xs >= 0 && xs < a.W) {
+      v = *reinterpret_cast<const uint4*>(x + ((size_t)n * HW + (size_t)ys * a.W + xs) * ld_x + c8 * 8);
+      if (act != PG_ACT_NONE) {
+        uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 f = unpack_bf16x2(w[i]);
+          w[i] = pack_bf16x2(pg_act_fwd(act, f.x), pg_act_fwd(act, f.y));
+        }
+        v = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+    }
+    *reinterpret_cast<uint4*>(out + (size_t)p * a.T * a.C + (size_t)t * a.C + c8 * 8) = v;
+  }
+}
+
+// dx[p, c] = act'(x_pre[p, c]) * sum_t dxcat[p - off_t, t*C + c]
+__global__ void __launch_bounds__(256)
+tap_scatter_kernel(const bf16* __restrict__ dxcat, const TapArgs a, int act, const bf16* __restrict__ x_pre,
+                   int64_t ld_pre, float* __restrict__ dx_f32, bf16* __restrict__ dx_bf16, int64_t ld_dx) {
+  const int c8n = a.C / 8;
+  const long long P = (long long)a.N * a.H * a.W;
+  const long long total = P * c8n;
+  const int HW = a.H * a.W;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(idx % c8n);
+    const long long p = idx / c8n;
+    const int n = (int)(p / HW), rem = (int)(p % HW);
+    const int y = rem / a.W, xx = rem % a.W;
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    for (int t = 0; t < a.T; ++t) {
+      const int ys = y - a.dy[t], xs = xx - a.dx[t];
+      if (ys < 0 || ys >= a.H || xs < 0 || xs >= a.W) continue;
+      const uint4 v = *reinterpret_cast<const uint4*>(dxcat + ((size_t)n * HW + (size_t)ys * a.W + xs) * a.T * a.C +
+                                                      (size_t)t * a.C + c8 * 8);
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = unpack_bf16x2(w[i]);
+        acc[2 * i] += f.x;
+        acc[2 * i + 1] += f.y;
+      }
+    }
+    if (act != PG_ACT_NONE) {
+      const uint4 v = *reinterpret_cast<const uint4*>(x_pre + (size_t)p * ld_pre + c8 * 8);
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = unpack_bf16x2(w[i]);
+        acc[2 * i] *= pg_act_bwd(act, f.x);
+        acc[2 * i + 1] *= pg_act_bwd(act, f.y);
+      }
+    }
+    if (dx_f32) {
+      float* o = dx_f32 + (size_t)p * ld_dx + c8 * 8;
+      *reinterpret_cast<float4*>(o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      *reinterpret_cast<float4*>(o + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    }
+    if (dx_bf16)
+      *reinterpret_cast<uint4*>(dx_bf16 + (size_t)p * ld_dx + c8 * 8) =
+          make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]),
+                     pack_bf16x2(acc[6], acc[7]));
+  }
+}
+
+int fill_taps(TapArgs& a, int N, int H, int W, int C, int T, const int* dy, const int* dx, const char* who) {
+  PG_REQUIRE(T >= 1 && T <= 32, "%s: %d taps (max 32)", who, T);
+  PG_REQUIRE(C % 8 == 0, "%s: channel count %d must be a multiple of 8", who, C);
+  a.N = N; a.H = H; a.W = W; a.C = C; a.T = T;
+  for (int t = 0; t < T; ++t) { a.dy[t] = dy[t]; a.dx[t] = dx[t]; }
+  return 0;
 }
 
 }  // namespace
 
 extern "C" int pg_conv_small_fwd(const float* x_nchw, const float* w_oihw, const float* bias, int N, int Cin, int H,
-                                 int W, int Cout, int kh, int kw, int pad_h, int pad_w, float* out_f32,
+                                 int W, int Cout, int kh, int kw, int pad_h, int pad_w, int pre_act, float* out_f32,
                                  void* out_bf16, int act_bf16, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   PG_REQUIRE(x_nchw && w_oihw && (out_f32 || out_bf16), "pg_conv_small_fwd: null argument");
-  ConvArgs a = {N, Cin, H, W, Cout, kh, kw, pad_h, pad_w, Cin * kh * kw};
+  ConvArgs a = {N, Cin, H, W, Cout, kh, kw, pad_h, pad_w, Cin * kh * kw, pre_act};
   PG_REQUIRE(a.K <= MAX_K, "pg_conv_small_fwd: Cin*kh*kw = %d exceeds %d", a.K, MAX_K);
   const long long P = (long long)N * H * W;
   const unsigned blocks = (unsigned)((P + PIX_PER_BLOCK - 1) / PIX_PER_BLOCK);
@@ -167,11 +274,11 @@ extern "C" int pg_conv_small_fwd(const float* x_nchw, const float* w_oihw, const
 }
 
 extern "C" int pg_conv_small_bwd(const float* x_nchw, const float* w_oihw, const float* dy_pm, int N, int Cin, int H,
-                                 int W, int Cout, int kh, int kw, int pad_h, int pad_w, float* dw_oihw, float* dbias,
-                                 float* dx_nchw, void* stream_) {
+                                 int W, int Cout, int kh, int kw, int pad_h, int pad_w, int pre_act, float* dw_oihw,
+                                 float* dbias, float* dx_nchw, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   PG_REQUIRE(x_nchw && w_oihw && dy_pm, "pg_conv_small_bwd: null argument");
-  ConvArgs a = {N, Cin, H, W, Cout, kh, kw, pad_h, pad_w, Cin * kh * kw};
+  ConvArgs a = {N, Cin, H, W, Cout, kh, kw, pad_h, pad_w, Cin * kh * kw, pre_act};
   PG_REQUIRE(a.K <= MAX_K, "pg_conv_small_bwd: Cin*kh*kw = %d exceeds %d", a.K, MAX_K);
   const long long P = (long long)N * H * W;
   if (dw_oihw) {
@@ -190,8 +297,41 @@ extern "C" int pg_conv_small_bwd(const float* x_nchw, const float* w_oihw, const
   }
   if (dx_nchw) {
     const long long threads = P * 32;
-    conv_small_dgrad_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(w_oihw, dy_pm, a, dx_nchw);
+    conv_small_dgrad_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(w_oihw, dy_pm, a, x_nchw, dx_nchw);
     if (pg_check_launch("pg_conv_small_bwd(dgrad)")) return 1;
   }
   return 0;
+}
+
+extern "C" int pg_tap_gather(const void* x_pm, int64_t ld_x, int N, int H, int W, int C, int T, const int* dy,
+                             const int* dx, int act, void* out, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  PG_REQUIRE(x_pm && out && dy && dx, "pg_tap_gather: null argument");
+  PG_REQUIRE(ld_x % 8 == 0, "pg_tap_gather: pitch must be a multiple of 8");
+  TapArgs a;
+  if (fill_taps(a, N, H, W, C, T, dy, dx, "pg_tap_gather")) return 1;
+  const long long total = (long long)N * H * W * T * (C / 8);
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)pg_num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  tap_gather_kernel<<<(unsigned)blocks, 256, 0, stream>>>((const bf16*)x_pm, ld_x, a, act, (bf16*)out);
+  return pg_check_launch("pg_tap_gather");
+}
+
+extern "C" int pg_tap_scatter(const void* dxcat, int N, int H, int W, int C, int T, const int* dy, const int* dx,
+                              int act, const void* x_pre, int64_t ld_pre, float* dx_f32, void* dx_bf16, int64_t ld_dx,
+                              void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  PG_REQUIRE(dxcat && dy && dx && (dx_f32 || dx_bf16), "pg_tap_scatter: null argument");
+  PG_REQUIRE(act == PG_ACT_NONE || x_pre, "pg_tap_scatter: activation backward needs the pre-activation input");
+  PG_REQUIRE(ld_dx % 8 == 0 && (act == PG_ACT_NONE || ld_pre % 8 == 0), "pg_tap_scatter: pitches must be multiples of 8");
+  TapArgs a;
+  if (fill_taps(a, N, H, W, C, T, dy, dx, "pg_tap_scatter")) return 1;
+  const long long total = (long long)N * H * W * (C / 8);
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)pg_num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  tap_scatter_kernel<<<(unsigned)blocks, 256, 0, stream>>>((const bf16*)dxcat, a, act, (const bf16*)x_pre, ld_pre, dx_f32,
+                                                            (bf16*)dx_bf16, ld_dx);
+  return pg_check_launch("pg_tap_scatter");
 }

@@ -413,7 +413,7 @@ __global__ void nchw_to_pm_kernel(const float* __restrict__ x, int C, int HW, TO
   }
 }
 template <typename TI>
-__global__ void pm_to_nchw_kernel(const TI* __restrict__ x, int64_t ld_x, int C, int HW, float* __restrict__ out) {
+__global__ void pm_to_nchw_kernel(const TI* __restrict__ x, int64_t ld_x, int C, int HW, int act, float* __restrict__ out) {
   __shared__ float tile[32][33];
   const int n = blockIdx.z;
   const int c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
@@ -429,7 +429,19 @@ __global__ void pm_to_nchw_kernel(const TI* __restrict__ x, int64_t ld_x, int C,
   __syncthreads();
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     const int c = c0 + i, p = p0 + threadIdx.x;
-    if (c < C && p < HW) out[((size_t)n * C + c) * HW + p] = tile[threadIdx.x][i];
+    if (c < C && p < HW) out[((size_t)n * C + c) * HW + p] = pg_act_fwd(act, tile[threadIdx.x][i]);
+  }
+}
+
+// g[p, c] = dy[p, c] * act'(pre[p, c]) -> bf16 (gradient through an activation applied to a conv output)
+__global__ void dact_mul_kernel(const bf16* __restrict__ dy, int64_t ld_dy, const float* __restrict__ pre, int64_t ld_pre,
+                                int P, int C, int act, bf16* __restrict__ out, int64_t ld_out) {
+  const long long total = (long long)P * C;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long r = idx / C;
+    const int c = (int)(idx % C);
+    out[r * ld_out + c] = __float2bfloat16(__bfloat162float(dy[r * ld_dy + c]) * pg_act_bwd(act, pre[r * ld_pre + c]));
   }
 }
 
@@ -593,13 +605,13 @@ extern "C" int pg_nchw_to_pm(const float* x_nchw, int N, int C, int HW, void* ou
   else nchw_to_pm_kernel<bf16><<<grid, block, 0, stream>>>(x_nchw, C, HW, (bf16*)out, ld_out);
   return pg_check_launch("pg_nchw_to_pm");
 }
-extern "C" int pg_pm_to_nchw(const void* x_pm, int x_is_f32, int64_t ld_x, int N, int C, int HW, float* out_nchw,
-                             void* stream_) {
+extern "C" int pg_pm_to_nchw(const void* x_pm, int x_is_f32, int64_t ld_x, int N, int C, int HW, int act,
+                             float* out_nchw, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   PG_REQUIRE(x_pm && out_nchw && N > 0 && C > 0 && HW > 0, "pg_pm_to_nchw: null/empty argument");
   dim3 grid((HW + 31) / 32, (C + 31) / 32, N), block(32, 8);
-  if (x_is_f32) pm_to_nchw_kernel<float><<<grid, block, 0, stream>>>((const float*)x_pm, ld_x, C, HW, out_nchw);
-  else pm_to_nchw_kernel<bf16><<<grid, block, 0, stream>>>((const bf16*)x_pm, ld_x, C, HW, out_nchw);
+  if (x_is_f32) pm_to_nchw_kernel<float><<<grid, block, 0, stream>>>((const float*)x_pm, ld_x, C, HW, act, out_nchw);
+  else pm_to_nchw_kernel<bf16><<<grid, block, 0, stream>>>((const bf16*)x_pm, ld_x, C, HW, act, out_nchw);
   return pg_check_launch("pg_pm_to_nchw");
 }
 extern "C" int pg_cast_f32_to_bf16(const float* x, void* y, int64_t numel, void* stream_) {
@@ -607,4 +619,13 @@ extern "C" int pg_cast_f32_to_bf16(const float* x, void* y, int64_t numel, void*
   PG_REQUIRE(x && y && numel > 0, "pg_cast_f32_to_bf16: null/empty argument");
   cast_kernel<<<grid_for(numel, 256), 256, 0, stream>>>(x, (bf16*)y, numel);
   return pg_check_launch("pg_cast_f32_to_bf16");
+}
+
+extern "C" int pg_dact_mul(const void* dy_bf16, int64_t ld_dy, const float* pre_f32, int64_t ld_pre, int P, int C, int act,
+                           void* out_bf16, int64_t ld_out, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  PG_REQUIRE(dy_bf16 && pre_f32 && out_bf16 && P > 0 && C > 0, "pg_dact_mul: null/empty argument");
+  dact_mul_kernel<<<grid_for((long long)P * C, 256), 256, 0, stream>>>((const bf16*)dy_bf16, ld_dy, pre_f32, ld_pre, P, C, act,
+                                                                      (bf16*)out_bf16, ld_out);
+  return pg_check_launch("pg_dact_mul");
 }

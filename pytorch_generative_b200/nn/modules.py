@@ -31,15 +31,15 @@ class _SmallConvFn(torch.autograd.Function):
     """Direct conv for image-channel inputs (Cin*kh*kw <= 160): NCHW in, NCHW out."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, padding):
+    def forward(ctx, x, weight, bias, padding, pre_act):
         x = x.contiguous().float()
         n, _, h, w = x.shape
         cout = weight.shape[0]
         out_pm = torch.empty(n * h * w, cout, dtype=F32, device=x.device)
         L.conv_small_fwd(x, weight.detach().contiguous(), None if bias is None else bias.detach(), padding,
-                         out_f32=out_pm)
+                         out_f32=out_pm, pre_act=pre_act)
         ctx.save_for_backward(x, weight)
-        ctx.padding, ctx.has_bias = padding, bias is not None
+        ctx.padding, ctx.has_bias, ctx.pre_act = padding, bias is not None, pre_act
         return ops.pm_to_nchw(out_pm, n, cout, h, w)
 
     @staticmethod
@@ -50,8 +50,9 @@ class _SmallConvFn(torch.autograd.Function):
         dw = torch.zeros_like(weight)
         db = torch.zeros(cout, dtype=F32, device=dy.device) if ctx.has_bias else None
         dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
-        L.conv_small_bwd(x, weight.detach().contiguous(), dy_pm, ctx.padding, dw=dw, dbias=db, dx=dx)
-        return dx, dw, db, None
+        L.conv_small_bwd(x, weight.detach().contiguous(), dy_pm, ctx.padding, dw=dw, dbias=db, dx=dx,
+                         pre_act=ctx.pre_act)
+        return dx, dw, db, None, None
 
 
 class CausalConv2d(nn.Conv2d):
@@ -70,7 +71,8 @@ class CausalConv2d(nn.Conv2d):
         mask[:, :, kh // 2, : kw // 2 + (0 if mask_center else 1)] = 1
         self.register_buffer("mask", mask)
 
-    def forward(self, x):
+    def forward(self, x, pre_act=L.ACT_NONE):
+        """`pre_act` (B200-path extension) fuses an activation applied to the conv's input."""
         _require_cuda(x, "CausalConv2d")
         self.weight.data *= self.mask
         cout, cin, kh, kw = self.weight.shape
@@ -80,10 +82,10 @@ class CausalConv2d(nn.Conv2d):
         if pad != (kh // 2, kw // 2):
             raise NotImplementedError("CausalConv2d: only 'same' padding (k//2) is on the path")
         if cin * kh * kw <= 160:
-            return _SmallConvFn.apply(x, self.weight, self.bias, pad)
-        from .tapconv import tap_conv2d  # wide-channel masked convs run on the tap-list GEMM kernel
+            return _SmallConvFn.apply(x, self.weight, self.bias, pad, pre_act)
+        from .tapconv import tap_conv2d  # wide-channel masked convs run as a tap list on the tcgen05 GEMM
 
-        return tap_conv2d(x, self.weight, self.bias, pad, live_mask=self.mask[0, 0])
+        return tap_conv2d(x, self.weight, self.bias, pad, pre_act=pre_act)
 
 
 # --------------------------------------------------------------------------------------------------

@@ -72,9 +72,9 @@ def nchw_to_pm(x, dtype, width=None):
     return out
 
 
-def pm_to_nchw(x_pm, n, c, h, w):
+def pm_to_nchw(x_pm, n, c, h, w, act=L.ACT_NONE):
     out = torch.empty(n, c, h, w, dtype=F32, device=x_pm.device)
-    L.pm_to_nchw(x_pm[:, :c] if x_pm.shape[1] != c else x_pm, out)
+    L.pm_to_nchw(x_pm[:, :c] if x_pm.shape[1] != c else x_pm, out, act=act)
     return out
 
 

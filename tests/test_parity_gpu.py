@@ -136,9 +136,15 @@ def _build(pg, cls, cfg, state, sample_fn=None):
     return m.to(dev())
 
 
-def test_image_gpt_matches_reference_fixture(pg):
-    fx = load("model_image_gpt.pt")
-    m = _build(pg, "ImageGPT", fx["cfg"], fx["state_before"])
+MODEL_FIXTURES = ["image_gpt", "pixel_cnn", "gated_pixel_cnn", "pixel_snail"]
+
+
+@pytest.mark.parametrize("name", MODEL_FIXTURES)
+def test_model_matches_reference_fixture(pg, name):
+    """Logits, recipe loss, every parameter gradient and the in-place weight masking against outputs of the
+    unmodified reference (tests/golden/make_golden.py)."""
+    fx = load(f"model_{name}.pt")
+    m = _build(pg, fx["cls"], fx["cfg"], fx["state_before"])
     x = fx["x"].to(dev())
     logits = m(x)
     assert logits.is_contiguous() and logits.shape == fx["logits"].shape
@@ -146,14 +152,19 @@ def test_image_gpt_matches_reference_fixture(pg):
     loss.backward()
     check("logits", logits, fx["logits"], TOL_BF16)
     assert abs(loss.item() - fx["loss"].item()) <= TOL_BF16 * abs(fx["loss"].item())
-    worst = {}
-    for name, p in m.named_parameters():
-        assert p.grad is not None, name
-        worst[name] = check("d" + name, p.grad, fx["grads"][name], TOL_BF16)
-    # state-dict round trip keeps the reference's keys, incl. the dynamic shape buffers
+    for pname, p in m.named_parameters():
+        if pname not in fx["grads"]:  # parameters the reference's graph never reaches (last layer's unused streams)
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, pname
+            continue
+        assert p.grad is not None, pname
+        check("d" + pname, p.grad, fx["grads"][pname], TOL_BF16)
+    # state-dict round trip keeps the reference's keys, incl. the dynamic shape buffers and the masked weights
     sd = m.state_dict()
     assert {"_c", "_h", "_w"} <= set(sd) and int(sd["_h"]) == x.shape[2]
-    assert torch.equal(sd["_input.weight"].cpu(), fx["state_after"]["_input.weight"])
+    assert set(sd) == set(fx["state_after"])
+    for k, v in fx["state_after"].items():
+        if k.endswith("weight") and (k[: -len("weight")] + "mask") in fx["state_after"]:
+            assert torch.equal(sd[k].cpu(), v), f"{k}: masked taps must be zeroed in place like the reference"
 
 
 @pytest.mark.parametrize("cfg,shape", [
@@ -203,14 +214,15 @@ def test_image_gpt_matches_oracle(pg, cfg, shape):
     assert worst <= TOL_BF16, "gradient parity:\n" + "\n".join(report)
 
 
-def test_image_gpt_sampling_follows_reference_raster_order(pg):
+@pytest.mark.parametrize("name", MODEL_FIXTURES)
+def test_sampling_follows_reference_raster_order(pg, name):
     """Same pre-drawn uniforms, consumed in raster order: pixels must be identical to the reference's sample
     except, at most, from a knife-edge draw (|u - p| within the bf16 tolerance) onwards."""
     from oracle import reference_path as O
 
-    fx = load("model_image_gpt.pt")
+    fx = load(f"model_{name}.pt")
     u = list(fx["sample_uniforms"])
-    m = _build(pg, "ImageGPT", fx["cfg"], fx["state_before"], sample_fn=O.uniform_sample_fn(u))
+    m = _build(pg, fx["cls"], fx["cfg"], fx["state_before"], sample_fn=O.uniform_sample_fn(u))
     m(fx["x"].to(dev()))  # registers _c/_h/_w like the reference
     n, c, h, w = fx["x"].shape
     got = m.sample(n_samples=n).cpu()
@@ -222,10 +234,82 @@ def test_image_gpt_sampling_follows_reference_raster_order(pg):
         r, col = divmod(first, w)
         canvas = ref.clone()
         canvas.view(n, c, -1)[:, :, first:] = -1
-        p_ref = torch.sigmoid(O.forward("image_gpt", fx["state_before"], canvas, fx["cfg"])[:, :, r, col])
+        p_ref = torch.sigmoid(O.forward(name, fx["state_before"], canvas, fx["cfg"])[:, :, r, col])
         margin = (u[first] - p_ref).abs().min().item()
         assert margin < 2e-2, f"samples diverge at pixel ({r},{col}) without a knife-edge draw (margin {margin:.3e})"
     # conditional sampling leaves given pixels untouched (reference models/tests.py:92-95)
     m._sample_fn = O.uniform_sample_fn(u)
     cs = m.sample(conditioned_on=fx["cond"].to(dev())).cpu()
     assert torch.equal(cs[:, :, : h // 2], fx["cond"][:, :, : h // 2])
+
+
+@pytest.mark.parametrize("name,cls,cfg,shape", [
+    ("pixel_cnn", "PixelCNN", dict(in_channels=1, out_channels=1, n_residual=3, residual_channels=32, head_channels=16),
+     (2, 1, 28, 28)),
+    ("gated_pixel_cnn", "GatedPixelCNN", dict(in_channels=3, out_channels=3, n_gated=3, gated_channels=32,
+                                              head_channels=16), (2, 3, 32, 32)),
+    ("pixel_snail", "PixelSNAIL", dict(in_channels=3, out_channels=3, n_channels=64, n_pixel_snail_blocks=2,
+                                       n_residual_blocks=2, attention_key_channels=16, attention_value_channels=32),
+     (2, 3, 32, 32)),
+])
+def test_conv_models_match_oracle(pg, name, cls, cfg, shape):
+    """Mid-size PixelCNN / GatedPixelCNN / PixelSNAIL (tap-list convs on the tensor-core GEMM, wide channels) against
+    the oracle: logits, recipe loss, and a fixed-cotangent VJP for every parameter."""
+    from oracle import reference_path as O
+
+    torch.manual_seed(0)
+    m = getattr(pg.models, cls)(**cfg)
+    g = torch.Generator().manual_seed(1)
+    with torch.no_grad():
+        for p in m.parameters():
+            p.add_(torch.randn(p.shape, generator=g) * 0.02)
+    state = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    x = (torch.bernoulli(torch.full(shape, 0.5), generator=g) if shape[1] == 1
+         else torch.randint(0, 256, shape, generator=g).float() / 255)
+    pt = O.trainable(state)
+    ref_logits = O.forward(name, pt, x, cfg)
+    ref_loss = O.recipe_loss(x, ref_logits).detach()
+    G = torch.randn(ref_logits.shape, generator=g) / ref_logits[0].numel()
+    (ref_logits * G).sum().backward()
+    ref_grads = {k: v.grad for k, v in pt.items() if v.requires_grad and v.grad is not None}
+    m = m.to(dev())
+    xd = x.to(dev())
+    logits = m(xd)
+    loss = _loss(xd, logits)
+    (logits * G.to(dev())).sum().backward()
+    check("logits", logits, ref_logits.detach(), TOL_BF16)
+    assert abs(loss.item() - ref_loss.item()) <= TOL_BF16 * abs(ref_loss.item())
+    report, worst = [], 0.0
+    for pname, p in m.named_parameters():
+        if pname not in ref_grads:
+            continue
+        gq, r = p.grad.detach().float().cpu(), ref_grads[pname]
+        e = (gq - r).abs().max().item() / max(1.0, r.abs().max().item())
+        report.append(f"{pname:50s} max-rel {e:.3e} |ref|max {r.abs().max().item():.3e}")
+        worst = max(worst, e)
+    assert worst <= TOL_BF16, "gradient parity:\n" + "\n".join(report)
+
+
+def test_wide_causal_conv2d_matches_oracle(pg):
+    """CausalConv2d with wide channels runs as a tap list on the GEMM (dense weight gradient over all 9 taps)."""
+    from oracle import reference_path as O
+
+    g = torch.Generator().manual_seed(3)
+    for mask_center in (False, True):
+        m = pg.nn.CausalConv2d(mask_center, in_channels=32, out_channels=48, kernel_size=3, padding=1)
+        x = torch.randn(2, 32, 12, 10, generator=g)
+        dy = torch.randn(2, 48, 12, 10, generator=g)
+        w0, b0 = m.weight.detach().clone(), m.bias.detach().clone()
+        xr, wr, br = x.clone().requires_grad_(True), w0.clone().requires_grad_(True), b0.clone().requires_grad_(True)
+        yr, w_masked = O.causal_conv2d(xr, wr, br, mask_center, 1)
+        gx, gw, gb = torch.autograd.grad(yr, [xr, wr, br], dy)
+        m = m.to(dev())
+        xd = x.to(dev()).requires_grad_(True)
+        y = m(xd)
+        y.backward(dy.to(dev()))
+        assert torch.equal(m.weight.detach().cpu(), w_masked.detach())
+        check("wide conv y", y, yr, TOL_BF16)
+        check("wide conv dx", xd.grad, gx, TOL_BF16)
+        check("wide conv dw", m.weight.grad, gw, TOL_BF16)
+        check("wide conv db", m.bias.grad, gb, TOL_BF16)
+        assert (m.weight.grad.cpu() * (1 - m.mask.cpu())).abs().sum() > 0  # masked taps receive gradient (dense wgrad)
