@@ -116,7 +116,7 @@ def run_ours(args):
     import torch.distributed as dist
 
     from pytorch_generative_b200 import _lib as L
-    from pytorch_generative_b200 import models
+    from pytorch_generative_b200 import models, parallel
 
     spec = CONFIGS[args.config]
     rank = int(os.environ.get("RANK", "0"))
@@ -136,13 +136,12 @@ def run_ours(args):
     torch.manual_seed(0)
     model = models.ImageGPT(**spec["cfg"]).to(dev)
     train_model = model
-    if world > 1:
-        train_model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], output_device=local_rank,
-                                                                broadcast_buffers=False, gradient_as_bucket_view=True)
+    parallel.broadcast_parameters(model)       # rank 0's weights everywhere (what DDP does at construction)
     params = [p for p in model.parameters()]
+    grad_avg = parallel.FlatGradAverager(params)  # one flat NCCL all-reduce per step; no-op at world size 1
     opt = torch.optim.Adam(params, lr=spec["lr"])
     sched = torch.optim.lr_scheduler.MultiplicativeLR(opt, lr_lambda=lambda _: 0.999977)
-    x_host = synthetic_batch(batch, spec["shape"], seed=rank).pin_memory()  # rank r uses seed r
+    x_host = synthetic_batch(batch, spec["shape"], seed=parallel.shard_seed(0, rank)).pin_memory()  # rank r: seed r
     x_dev = x_host.to(dev)
 
     def step(x):
@@ -151,6 +150,7 @@ def run_ours(args):
         preds = train_model(x)
         loss = recipe_loss(x, None, preds)
         loss.backward()
+        grad_avg.average_()
         norm = torch.nn.utils.clip_grad_norm_(params, 1e50)
         opt.step()
         sched.step()
