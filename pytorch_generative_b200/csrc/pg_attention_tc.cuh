@@ -251,12 +251,20 @@ attn_fwd_tc_kernel(const __grid_constant__ AttnTmaps tm, const AttnArgs a, const
 // ------------------------------------------------------------------------------------------------
 // Backward
 // ------------------------------------------------------------------------------------------------
+// Thread layout (320 threads): warps 0-3 = softmax group A (key columns 0-63 of the tile), warps 4-7 = group B
+// (columns 64-127); thread = query row (TMEM lane) in both groups.  Warp 8 = TMA producer, warp 9 = TMEM owner + MMA
+// issuer.  Per query tile there are exactly two hand-offs:
+//   MMA phase    : dV += P^T dO, dK += dS^T Q, dQ = dS K  (tile i)   then   S = Q K^T, dP = dO V^T  (tile i+1)
+//   thread phase : read out dQ(i) (-> fp32 staging -> TMA reduce-add), then softmax / dS of tile i+1
+// so the tensor core runs five MMAs back to back and the exp/convert work of the 256 softmax threads is the only
+// other serial stage.
 template <int DV>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 attn_bwd_tc_kernel(const __grid_constant__ AttnTmaps tm, const AttnArgs a, const int T) {
   constexpr int V_BYTES = DV * 256;
   constexpr int TMEM_COLS = 512;
   constexpr int COL_S = 0, COL_DP = 128, COL_DV = 256, COL_DK = 384, COL_DQ = 448;
+  constexpr bool DQ_OWN_STAGING = (DV == 64);  // DV = 128 has no smem left: dQ staging aliases sP
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sK = smem;
   uint8_t* sV = sK + ATOM_BYTES;
@@ -264,13 +272,13 @@ attn_bwd_tc_kernel(const __grid_constant__ AttnTmaps tm, const AttnArgs a, const
   uint8_t* sdO = sQ + 2 * ATOM_BYTES;    // 2 stages
   uint8_t* sP = sdO + 2 * V_BYTES;       // 2 atoms
   uint8_t* sdS = sP + 2 * ATOM_BYTES;    // 2 atoms
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sdS + 2 * ATOM_BYTES);
+  uint8_t* sdQ = DQ_OWN_STAGING ? sdS + 2 * ATOM_BYTES : sP;  // fp32 [2 slabs][128][32]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sdS + 2 * ATOM_BYTES + (DQ_OWN_STAGING ? 2 * ATOM_BYTES : 0));
   uint64_t* kv_full = bars;
   uint64_t* qdo_full = bars + 1;   // [2]
   uint64_t* qdo_empty = bars + 3;  // [2]
-  uint64_t* s_full = bars + 5;     // S and dP complete
-  uint64_t* pds_full = bars + 6;   // P and dS written to smem
-  uint64_t* dq_full = bars + 7;    // dQ (and everything before it) complete
+  uint64_t* s_full = bars + 5;     // S/dP of the next tile (and dQ of the previous one) complete
+  uint64_t* pds_full = bars + 6;   // P and dS written to smem (256 arrivals)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -284,18 +292,17 @@ attn_bwd_tc_kernel(const __grid_constant__ AttnTmaps tm, const AttnArgs a, const
     mbar_init(kv_full, 1);
     for (int s = 0; s < 2; ++s) { mbar_init(&qdo_full[s], 1); mbar_init(&qdo_empty[s], 1); }
     mbar_init(s_full, 1);
-    mbar_init(pds_full, 128);
-    mbar_init(dq_full, 1);
+    mbar_init(pds_full, 256);
     fence_barrier_init();
     fence_proxy_async_smem();
   }
-  if (warp == 5) tmem_alloc<TMEM_COLS>(tmem_slot);
+  if (warp == 9) tmem_alloc<TMEM_COLS>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == 4) {
+  if (warp == 8) {
     if (lane == 0) {
       mbar_arrive_expect_tx(kv_full, ATOM_BYTES + V_BYTES);
       tma_load_3d(sK, &tm.k, kv_full, h * 64, j * AT, n);
@@ -311,7 +318,7 @@ attn_bwd_tc_kernel(const __grid_constant__ AttnTmaps tm, const AttnArgs a, const
           tma_load_3d(sdO + st * V_BYTES + v * ATOM_BYTES, &tm.d_o, &qdo_full[st], h * DV + v * 64, i * AT, n);
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     if (lane == 0) {
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);   // S = Q K^T, dP = dO V^T
       constexpr uint32_t idesc_dv = umma_idesc_bf16(128, DV, 1, 1);   // dV += P^T dO
@@ -326,12 +333,12 @@ attn_bwd_tc_kernel(const __grid_constant__ AttnTmaps tm, const AttnArgs a, const
 #pragma unroll
         for (int kk = 0; kk < DV / 16; ++kk)
           umma_bf16_ss(tmem + COL_DP, desc_kmajor(do_addr, kk), desc_kmajor(v_addr, kk), idesc_s, kk > 0);
-        umma_commit(s_full);
       };
       mbar_wait(kv_full, 0);
       mbar_wait(&qdo_full[0], 0);
       tc_fence_after();
       issue_s_dp(0);
+      umma_commit(s_full);
       for (int it = 0; it < niter; ++it) {
         const int st = it & 1;
         const uint32_t q_addr = smem_u32(sQ + st * ATOM_BYTES), do_addr = smem_u32(sdO + st * V_BYTES);
@@ -346,28 +353,49 @@ attn_bwd_tc_kernel(const __grid_constant__ AttnTmaps tm, const AttnArgs a, const
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)  // K = 128 keys
           umma_bf16_ss(tmem + COL_DQ, desc_kmajor(ds_addr, kk), desc_mnmajor(k_addr, kk), idesc_dq, kk > 0);
-        umma_commit(dq_full);
-        umma_commit(&qdo_empty[st]);
+        umma_commit(&qdo_empty[st]);  // Q_i / dO_i stage reusable once these complete
         if (it + 1 < niter) {
           mbar_wait(&qdo_full[st ^ 1], ((it + 1) >> 1) & 1);
           tc_fence_after();
           issue_s_dp(st ^ 1);
         }
+        umma_commit(s_full);  // dQ(it) [+ S/dP(it+1)] complete
       }
     }
   } else {
-    // ===================== thread == query row =====================
-    const int r = warp * 32 + lane;
-    const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+    // ===================== softmax groups: thread == query row, group == key-column half =====================
+    const int grp = warp >> 2;              // 0: columns 0-63, 1: columns 64-127
+    const int r = (warp & 3) * 32 + lane;   // TMEM lane / tile row
+    const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
     const float sl2 = a.scale * 1.4426950408889634f;
     const int k0 = j * AT;
-    // row statistics are fetched one iteration ahead so their global-load latency hides behind the MMAs
     const size_t stat_base = ((size_t)n * a.H + h) * a.S;
     float lse_next = 0.f, delta_next = 0.f;
     if (j * AT + r < a.S) {
       lse_next = a.lse_in[stat_base + j * AT + r];
       delta_next = a.delta[stat_base + j * AT + r];
     }
+    // dQ of tile i: this group's 32 columns -> fp32 staging slab -> (both groups done) one bulk reduce-add per slab
+    auto flush_dq = [&](int i) {
+      if (threadIdx.x == 0) tma_store_wait_read<0>();  // previous reduce has drained the staging slabs
+      __syncwarp();
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(tmem + COL_DQ + lane_base + grp * 32, v);
+      tmem_wait_ld();
+      slab32_store_scaled(sdQ + grp * ATOM_BYTES, r, v, a.scale);
+      fence_proxy_async_smem();
+      tc_fence_before();
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (threadIdx.x == 0) {
+        tma_reduce_add_3d(&tm.dq, sdQ, h * 64, i * AT, n);
+        tma_reduce_add_3d(&tm.dq, sdQ + ATOM_BYTES, h * 64 + 32, i * AT, n);
+        tma_store_commit();
+        if (!DQ_OWN_STAGING) tma_store_wait_read<0>();  // staging aliases sP: must be drained before P is written
+      }
+      __syncwarp();
+      if (!DQ_OWN_STAGING) asm volatile("bar.sync 1, 256;" ::: "memory");
+    };
     for (int it = 0; it < niter; ++it) {
       const int i = j + it;
       const int qi = i * AT + r;
@@ -385,12 +413,10 @@ attn_bwd_tc_kernel(const __grid_constant__ AttnTmaps tm, const AttnArgs a, const
       const bool need_mask = (it == 0) || (i == T - 1);
       mbar_wait(s_full, it & 1);
       tc_fence_after();
-      // sP doubles as the fp32 staging tile of the previous iteration's dQ reduce: it must have been read out
-      if (r == 0) tma_store_wait_read<0>();
-      __syncwarp();
-      attn_bar_sync();
+      if (it > 0) flush_dq(i - 1);
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c = grp * 2 + cc;
         uint32_t sv[32], dv[32];
         tmem_ld_32x32b_x32(tmem + COL_S + lane_base + c * 32, sv);
         tmem_ld_32x32b_x32(tmem + COL_DP + lane_base + c * 32, dv);
@@ -415,35 +441,20 @@ attn_bwd_tc_kernel(const __grid_constant__ AttnTmaps tm, const AttnArgs a, const
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(pds_full);
-      mbar_wait(dq_full, it & 1);
-      tc_fence_after();
-      // dQ_i tile -> fp32 slabs in sP (free: all MMAs of this iteration are complete) -> one bulk reduce-add
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(tmem + COL_DQ + lane_base + c * 32, v);
-        tmem_wait_ld();
-        slab32_store_scaled(sP + c * ATOM_BYTES, r, v, a.scale);
-      }
-      fence_proxy_async_smem();
-      attn_bar_sync();
-      if (r == 0) {
-        tma_reduce_add_3d(&tm.dq, sP, h * 64, i * AT, n);
-        tma_reduce_add_3d(&tm.dq, sP + ATOM_BYTES, h * 64 + 32, i * AT, n);
-        tma_store_commit();
-      }
-      __syncwarp();
-      tc_fence_before();
     }
-    if (r == 0) tma_store_wait<0>();
+    mbar_wait(s_full, niter & 1);  // last dQ (and all dV / dK accumulation) complete
+    tc_fence_after();
+    flush_dq(j + niter - 1);
+    if (threadIdx.x == 0) tma_store_wait<0>();
     __syncwarp();
-    // dV_j, dK_j are complete (the last dq_full commit covers all earlier MMAs); thread == key row.
-    // TMEM loads are warp-aligned instructions: every lane executes them, only the stores are predicated.
+    // dV_j, dK_j: thread == key row; each group writes its half of the columns.  TMEM loads are warp-aligned:
+    // every lane executes them, only the stores are predicated.
     const int kj = k0 + r;
     const bool key_ok = kj < a.S;
     bf16* dvrow = a.dv_out + ((size_t)n * a.S + kj) * a.ld_dv + h * DV;
 #pragma unroll
-    for (int c = 0; c < DV / 32; ++c) {
+    for (int cc = 0; cc < DV / 64; ++cc) {
+      const int c = grp * (DV / 64) + cc;
       uint32_t v[32];
       tmem_ld_32x32b_x32(tmem + COL_DV + lane_base + c * 32, v);
       tmem_wait_ld();
@@ -458,8 +469,8 @@ attn_bwd_tc_kernel(const __grid_constant__ AttnTmaps tm, const AttnArgs a, const
       }
     }
     bf16* dkrow = a.dk_out + ((size_t)n * a.S + kj) * a.ld_dk + h * 64;
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
+    {
+      const int c = grp;
       uint32_t v[32];
       tmem_ld_32x32b_x32(tmem + COL_DK + lane_base + c * 32, v);
       tmem_wait_ld();
@@ -476,7 +487,7 @@ attn_bwd_tc_kernel(const __grid_constant__ AttnTmaps tm, const AttnArgs a, const
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == 9) {
     tc_fence_after();
     tmem_dealloc<TMEM_COLS>(tmem);
   }
@@ -550,13 +561,13 @@ int attn_bwd_tc(const AttnArgs& a, cudaStream_t stream) {
   const int T = (a.S + AT - 1) / AT;
   const unsigned grid = (unsigned)(a.N * a.H * T);
   if (a.dv == 64) {
-    constexpr int SMEM = ATOM_BYTES * (1 + 1 + 2 + 2 + 2 + 2) + 256;
+    constexpr int SMEM = ATOM_BYTES * (1 + 1 + 2 + 2 + 2 + 2 + 2) + 256;  // + 2 atoms of fp32 dQ staging
     PG_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    attn_bwd_tc_kernel<64><<<grid, 192, SMEM, stream>>>(tm, a, T);
+    attn_bwd_tc_kernel<64><<<grid, 320, SMEM, stream>>>(tm, a, T);
   } else {
     constexpr int SMEM = ATOM_BYTES * (1 + 2 + 2 + 4 + 2 + 2) + 256;
     PG_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    attn_bwd_tc_kernel<128><<<grid, 192, SMEM, stream>>>(tm, a, T);
+    attn_bwd_tc_kernel<128><<<grid, 320, SMEM, stream>>>(tm, a, T);
   }
   if (pg_check_launch("pg_causal_attn_bwd(tcgen05)")) return 1;
   const long long P = (long long)a.N * a.S;

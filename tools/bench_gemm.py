@@ -21,7 +21,10 @@ def timeit(fn, reps=10):
     return ts[len(ts) // 2]
 
 rows = []
+ONLY = os.environ.get("PG_CASES")
 def case(name, M, N, K, **kw):
+    if ONLY and not any(t in name for t in ONLY.split(",")):
+        return
     a_mn, b_mn = kw.get("a_mn", False), kw.get("b_mn", False)
     A = torch.randn((K, M) if a_mn else (M, K), device=dev).bfloat16()
     B = torch.randn((K, N) if b_mn else (N, K), device=dev).bfloat16()
