@@ -414,24 +414,29 @@ attn_bwd_tc_kernel(const __grid_constant__ AttnTmaps tm, const AttnArgs a, const
       mbar_wait(s_full, it & 1);
       tc_fence_after();
       if (it > 0) flush_dq(i - 1);
-#pragma unroll 1
+      // all four TMEM loads of this thread's 64 columns are issued before the single wait (ILP: the exp / convert
+      // chains of the two chunks then interleave), results go to the swizzled P / dS tiles
+      uint32_t sv[2][32], dv[2][32];
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        tmem_ld_32x32b_x32(tmem + COL_S + lane_base + (grp * 2 + cc) * 32, sv[cc]);
+        tmem_ld_32x32b_x32(tmem + COL_DP + lane_base + (grp * 2 + cc) * 32, dv[cc]);
+      }
+      tmem_wait_ld();
+#pragma unroll
       for (int cc = 0; cc < 2; ++cc) {
         const int c = grp * 2 + cc;
-        uint32_t sv[32], dv[32];
-        tmem_ld_32x32b_x32(tmem + COL_S + lane_base + c * 32, sv);
-        tmem_ld_32x32b_x32(tmem + COL_DP + lane_base + c * 32, dv);
-        tmem_wait_ld();
         uint32_t pw[16], dw[16];
 #pragma unroll
         for (int e = 0; e < 32; e += 2) {
-          float p0 = fast_exp2(fmaf(__uint_as_float(sv[e]), sl2, -lse2));
-          float p1 = fast_exp2(fmaf(__uint_as_float(sv[e + 1]), sl2, -lse2));
+          float p0 = fast_exp2(fmaf(__uint_as_float(sv[cc][e]), sl2, -lse2));
+          float p1 = fast_exp2(fmaf(__uint_as_float(sv[cc][e + 1]), sl2, -lse2));
           if (need_mask) {
             if (k0 + c * 32 + e > qlim) p0 = 0.f;
             if (k0 + c * 32 + e + 1 > qlim) p1 = 0.f;
           }
-          const float d0 = p0 * (__uint_as_float(dv[e]) - delta);
-          const float d1 = p1 * (__uint_as_float(dv[e + 1]) - delta);
+          const float d0 = p0 * (__uint_as_float(dv[cc][e]) - delta);
+          const float d1 = p1 * (__uint_as_float(dv[cc][e + 1]) - delta);
           pw[e >> 1] = pack_bf16x2(p0, p1);
           dw[e >> 1] = pack_bf16x2(d0, d1);
         }
