@@ -15,6 +15,7 @@
 // tensors where they lie: no transposed copies of activations or weights are ever materialised.
 //
 // Replaces: every 1x1 nn.Conv2d forward/backward on the reference path (see include/pg_b200.h).
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/pg_b200.h"
@@ -193,11 +194,18 @@ __device__ __forceinline__ void slab_bf16_store(uint8_t* slab, int r, const floa
 // ------------------------------------------------------------------------------------------------
 // tcgen05 kernel
 // ------------------------------------------------------------------------------------------------
-template <int BN, bool A_MN, bool B_MN>
+// TWO = cta_group::2: the two CTAs of a cluster pair compute one 256 x BN tile; each stages its own 128 rows of A and
+// its half (BN/2 rows) of B, the leader issues M = 256 MMAs that read both CTAs' shared memory, each CTA owns the
+// accumulator rows of its half in its own TMEM and runs its own epilogue.  Halves the L2 -> SM operand traffic per flop
+// (64 instead of 96 B/cycle/SM at BN = 256), which is what bounds the 1-CTA kernel.
+template <int BN, bool A_MN, bool B_MN, bool TWO>
 __global__ void __launch_bounds__(384, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ EpiMaps em, const GemmParams p) {
-  constexpr int B_STAGE_BYTES = BN * BK * 2;
+  static_assert(!TWO || (!A_MN && BN == 256), "the 2-CTA kernel is the K-major-A, 256-wide variant");
+  constexpr int B_ROWS = TWO ? BN / 2 : BN;  // rows of B (N extent) staged by this CTA
+  constexpr int B_STAGE_BYTES = B_ROWS * BK * 2;
+  constexpr int MT = TWO ? 2 * BM : BM;      // M extent of a tile
   constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   constexpr int ACC_STAGES = 2;
   constexpr int TMEM_COLS = (ACC_STAGES * BN <= 32) ? 32
@@ -220,6 +228,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t rank = TWO ? cluster_ctarank() : 0u;          // 0 = leader of the CTA pair
+  const int tile_first = TWO ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tile_stride = TWO ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -232,15 +243,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int i = 0; i < ACC_STAGES; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 8);  // one arrive per epilogue warp (2 groups x 4)
+      mbar_init(&tempty_bar[i], TWO ? 16 : 8);  // one arrive per epilogue warp (2 groups x 4), of both CTAs if paired
     }
     for (int i = 0; i < 4; ++i) mbar_init(&in_full[i], 1);
     fence_barrier_init();
     fence_proxy_async_smem();
   }
-  if (warp == 2) tmem_alloc<TMEM_COLS>(tmem_slot);
+  if (warp == 2) {
+    if (TWO) tmem_alloc_2sm<TMEM_COLS>(tmem_slot);
+    else tmem_alloc<TMEM_COLS>(tmem_slot);
+  }
   tc_fence_before();
   __syncthreads();
+  if (TWO) cluster_sync_all();  // both CTAs' barriers are initialised before any cross-CTA signal
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -251,7 +266,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // ===================== TMA producer =====================
       int s = 0;
       uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = tile_first; tile < num_tiles; tile += tile_stride) {
         const int n_blk = tile % p.num_n_blk;
         const int rest = tile / p.num_n_blk;
         const int m_blk = rest % p.num_m_blk;
@@ -262,6 +277,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* sA = smem + s * STAGE_BYTES;
           uint8_t* sB = sA + A_STAGE_BYTES;
+          if (TWO) {
+            // both CTAs load their halves; all bytes are accounted on the leader's barrier
+            if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * STAGE_BYTES);
+            const int row0 = m_blk * MT + rank * BM, nb0 = n_blk * BN + rank * B_ROWS;
+            tma_load_2d_2sm(sA, &tmA, &full_bar[s], kit * BK, row0);
+            if (!B_MN) {
+              tma_load_2d_2sm(sB, &tmB, &full_bar[s], kit * BK, nb0);
+            } else {
+#pragma unroll
+              for (int j = 0; j < B_ROWS / 64; ++j)
+                tma_load_2d_2sm(sB + j * (BK * 128), &tmB, &full_bar[s], nb0 + j * 64, kit * BK);
+            }
+            if (++s == STAGES) { s = 0; ph ^= 1; }
+            continue;
+          }
           mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
           if (!A_MN) {
             tma_load_2d(sA, &tmA, &full_bar[s], kit * BK, m_blk * BM);  // box {64 k, 128 rows}
@@ -282,14 +312,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===================== MMA issuer =====================
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+    if (lane == 0 && rank == 0) {
+      // ===================== MMA issuer (leader CTA only when paired) =====================
+      constexpr uint32_t idesc = umma_idesc_bf16(MT, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
       int s = 0;
       uint32_t ph = 0;
       int as = 0;
       uint32_t aph = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = tile_first; tile < num_tiles; tile += tile_stride) {
         const int rest = tile / p.num_n_blk;
         const int ks = rest / p.num_m_blk;
         const int k0 = ks * p.k_per_split;
@@ -310,12 +340,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                          : umma_desc_sw128(a_addr + kk * 32, 16, 1024);
             const uint64_t b_desc = B_MN ? umma_desc_sw128(b_addr + kk * 2048, BK * 128, 1024)
                                          : umma_desc_sw128(b_addr + kk * 32, 16, 1024);
-            umma_bf16_ss(d_tmem, a_desc, b_desc, idesc, (kit > k0 || kk > 0) ? 1u : 0u);
+            if (TWO) umma_bf16_ss_2sm(d_tmem, a_desc, b_desc, idesc, (kit > k0 || kk > 0) ? 1u : 0u);
+            else umma_bf16_ss(d_tmem, a_desc, b_desc, idesc, (kit > k0 || kk > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs have read it
+          // frees the smem stage (in both CTAs when paired) once these MMAs have read it
+          if (TWO) umma_commit_2sm(&empty_bar[s]);
+          else umma_commit(&empty_bar[s]);
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
-        umma_commit(&tfull_bar[as]);  // accumulator complete -> epilogue
+        // accumulator complete -> epilogue(s)
+        if (TWO) umma_commit_2sm(&tfull_bar[as]);
+        else umma_commit(&tfull_bar[as]);
         if (++as == ACC_STAGES) { as = 0; aph ^= 1; }
       }
     }
@@ -341,7 +376,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     auto issue_inputs = [&](int tile, int c, int st) {  // group leader only
       const int n_blk = tile % p.num_n_blk;
       const int m_blk = (tile / p.num_n_blk) % p.num_m_blk;
-      const int col0 = n_blk * BN + c * 32, row0 = m_blk * BM;
+      const int col0 = n_blk * BN + c * 32, row0 = m_blk * MT + (int)rank * BM;
       uint8_t* b = grp_base + st * p.epi_stage_bytes;
       uint64_t* bar = &in_full[grp * 2 + st];
       mbar_arrive_expect_tx(bar, p.in_bytes);
@@ -351,7 +386,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     };
     // chunk at sequence position `pos` -> (tile, chunk)
     auto prefetch_pos = [&](unsigned pos, int st) {
-      const int t = blockIdx.x + (int)(pos / NCH) * (int)gridDim.x;
+      const int t = tile_first + (int)(pos / NCH) * tile_stride;
       if (t < num_tiles) issue_inputs(t, (int)(pos % NCH), st);
     };
     if (p.staged && p.in_bytes > 0 && leader) {
@@ -360,14 +395,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     __syncwarp();
 
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = tile_first; tile < num_tiles; tile += tile_stride) {
       const int n_blk = tile % p.num_n_blk;
       const int rest = tile / p.num_n_blk;
       const int m_blk = rest % p.num_m_blk;
       const int ks = rest / p.num_m_blk;
       mbar_wait(&tfull_bar[as], aph);
       tc_fence_after();
-      const int row = m_blk * BM + r;
+      const int row = m_blk * MT + (int)rank * BM + r;
 #pragma unroll 1
       for (int c = 0; c < NCH; ++c, ++gc) {
         if ((gc & 1u) != (unsigned)grp) continue;  // the other group's chunk
@@ -436,7 +471,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         fence_proxy_async_smem();
         asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
         if (leader) {
-          const int row0 = m_blk * BM;
+          const int row0 = m_blk * MT + (int)rank * BM;
           if (p.off_outf >= 0) {
             if (e.accumulate) tma_reduce_add_2d(&em.out_f32, base + p.off_outf, col0, row0);
             else tma_store_2d(&em.out_f32, base + p.off_outf, col0, row0);
@@ -451,7 +486,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      if (lane == 0) {
+        if (TWO && rank != 0) mbar_arrive_cluster(&tempty_bar[as], 0);  // the leader's MMA waits for both epilogues
+        else mbar_arrive(&tempty_bar[as]);
+      }
       if (++as == ACC_STAGES) { as = 0; aph ^= 1; }
     }
     if (p.staged && leader) tma_store_wait<0>();
@@ -459,9 +497,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   tc_fence_before();
   __syncthreads();
+  if (TWO) cluster_sync_all();  // neither CTA may exit (or free TMEM) while its partner can still signal / read it
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc<TMEM_COLS>(tmem_base);
+    if (TWO) tmem_dealloc_2sm<TMEM_COLS>(tmem_base);
+    else tmem_dealloc<TMEM_COLS>(tmem_base);
   }
 }
 
@@ -493,8 +533,10 @@ __global__ void gemm_simt_kernel(const bf16* __restrict__ A, int a_mn, int64_t l
   epilogue_row32(p, row, col0, ncols, true, accu);
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, bool TWO = false>
 int launch_tc(const void* A, int64_t lda, const void* B, int64_t ldb, GemmParams& p, cudaStream_t stream) {
+  constexpr int B_ROWS = TWO ? BN / 2 : BN;
+  if (TWO) p.num_m_blk = (p.M + 2 * BM - 1) / (2 * BM);
   CUtensorMap tmA, tmB;
   if (!A_MN) {
     if (pg_make_tmap_2d_bf16(&tmA, A, p.M, p.K, lda, BM, BK)) return 1;
@@ -502,11 +544,11 @@ int launch_tc(const void* A, int64_t lda, const void* B, int64_t ldb, GemmParams
     if (pg_make_tmap_2d_bf16(&tmA, A, p.K, p.M, lda, BK, 64)) return 1;
   }
   if (!B_MN) {
-    if (pg_make_tmap_2d_bf16(&tmB, B, p.N, p.K, ldb, BN, BK)) return 1;
+    if (pg_make_tmap_2d_bf16(&tmB, B, p.N, p.K, ldb, B_ROWS, BK)) return 1;
   } else {
     if (pg_make_tmap_2d_bf16(&tmB, B, p.K, p.N, ldb, BK, 64)) return 1;
   }
-  constexpr int STAGE_BYTES = A_STAGE_BYTES + BN * BK * 2;
+  constexpr int STAGE_BYTES = A_STAGE_BYTES + B_ROWS * BK * 2;
   const pg_gemm_epilogue& e = p.epi;
   EpiMaps em;
   memset(&em, 0, sizeof(em));
@@ -545,12 +587,31 @@ int launch_tc(const void* A, int64_t lda, const void* B, int64_t ldb, GemmParams
   PG_REQUIRE(stages >= 2, "pg_gemm_bf16: epilogue staging leaves no room for the operand pipeline (BN=%d)", BN);
   p.stages = stages;
   const int smem_bytes = stages * STAGE_BYTES + fixed;
-  auto kern = gemm_tc_kernel<BN, A_MN, B_MN>;
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, TWO>;
   PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
   const int num_tiles = p.num_m_blk * p.num_n_blk * p.splits;
-  const int grid = min(num_tiles, pg_num_sms());
-  kern<<<grid, 384, smem_bytes, stream>>>(tmA, tmB, em, p);
-  return pg_check_launch("pg_gemm_bf16(tcgen05)");
+  if (!TWO) {
+    const int grid = min(num_tiles, pg_num_sms());
+    kern<<<grid, 384, smem_bytes, stream>>>(tmA, tmB, em, p);
+    return pg_check_launch("pg_gemm_bf16(tcgen05)");
+  }
+  // CTA pairs: clusters of 2 along x, one pair per tile stream
+  int pairs = pg_num_sms() / 2;
+  if (pairs > num_tiles) pairs = num_tiles;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(384);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  PG_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, em, p));
+  return pg_check_launch("pg_gemm_bf16(tcgen05, cta_group::2)");
 }
 
 template <bool A_MN, bool B_MN>
@@ -574,6 +635,12 @@ int dispatch_bn(const void* A, int64_t lda, const void* B, int64_t ldb, GemmPara
     if (bn == 256 && ((p.M + BM - 1) / BM) * ((p.N + 255) / 256) * p.splits < pg_num_sms() && p.N % 256 != 0) bn = 128;
   }
   p.num_n_blk = (p.N + bn - 1) / bn;
+  if constexpr (!A_MN) {
+    // CTA pairs for the big pixel-major GEMMs (forward / dgrad): 256 x 256 tiles, enough of them to fill 74 pairs
+    static const bool no_pairs = getenv("PG_GEMM_NO_PAIRS") != nullptr;
+    if (!no_pairs && bn == 256 && p.splits == 1 && ((p.M + 255) / 256) * p.num_n_blk >= pg_num_sms() / 2)
+      return launch_tc<256, false, B_MN, true>(A, lda, B, ldb, p, stream);
+  }
   switch (bn) {
     case 256: return launch_tc<256, A_MN, B_MN>(A, lda, B, ldb, p, stream);
     case 128: return launch_tc<128, A_MN, B_MN>(A, lda, B, ldb, p, stream);

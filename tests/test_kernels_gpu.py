@@ -56,6 +56,8 @@ def assert_close(name, got, ref, rtol, atol=0.0):
 GEMM_SHAPES = [
     (128, 128, 64), (128, 256, 64), (256, 256, 128), (384, 64, 192), (1000, 200, 72), (130, 24, 512),
     (4096, 512, 512), (2048, 1536, 512), (1024, 2048, 512), (2048, 512, 2048), (4096, 3, 512), (777, 136, 264),
+    # large enough for the cta_group::2 (CTA-pair) kernel: >= 74 tiles of 256 x 256, with M / N / K tails
+    (16384, 512, 512), (8192, 1536, 256), (10000, 768, 320), (19000, 264, 72),
 ]
 
 
@@ -119,7 +121,7 @@ def _dgelu(x):
 
 
 @pytest.mark.parametrize("impl", [0, 1])
-@pytest.mark.parametrize("shape", [(512, 2048, 512), (1000, 200, 72)])
+@pytest.mark.parametrize("shape", [(512, 2048, 512), (1000, 200, 72), (9600, 2048, 128)])
 def test_gemm_epilogue_forward(L, shape, impl):
     """bias + residuals -> fp32 'pre', bf16 'pre', bf16 gelu(pre): the fused FC1/proj epilogues."""
     M, N, K = shape
@@ -142,9 +144,10 @@ def test_gemm_epilogue_forward(L, shape, impl):
 
 
 @pytest.mark.parametrize("impl", [0, 1])
-def test_gemm_epilogue_dact(L, impl):
-    """dgrad through GELU: out = (dY·W) * gelu'(u)."""
-    M, N, K = 640, 512, 256
+@pytest.mark.parametrize("M", [640, 19200])
+def test_gemm_epilogue_dact(L, impl, M):
+    """dgrad through GELU: out = (dY·W) * gelu'(u)  (M = 19200 runs on CTA pairs)."""
+    N, K = 512, 256
     A, B, acc = _operands(M, N, K, False, True, seed=3)
     u = torch.randn(M, N, generator=torch.Generator().manual_seed(4)).to(_dev()).bfloat16()
     out = torch.empty(M, N, device=_dev(), dtype=torch.bfloat16)
