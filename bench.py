@@ -116,7 +116,7 @@ def run_ours(args):
     import torch.distributed as dist
 
     from pytorch_generative_b200 import _lib as L
-    from pytorch_generative_b200 import models, parallel
+    from pytorch_generative_b200 import losses, models, parallel
 
     spec = CONFIGS[args.config]
     rank = int(os.environ.get("RANK", "0"))
@@ -148,7 +148,7 @@ def run_ours(args):
         train_model.train()
         opt.zero_grad()
         preds = train_model(x)
-        loss = recipe_loss(x, None, preds)
+        loss = losses.bce_with_logits_sum_mean(preds, x)  # the recipes' loss_fn (image_gpt.py:158-162), fused kernel
         loss.backward()
         grad_avg.average_()
         norm = torch.nn.utils.clip_grad_norm_(params, 1e50)

@@ -128,9 +128,25 @@ def test_positional_encoding_bit_identical(pg):
 # ImageGPT against the reference fixture and the oracle
 # --------------------------------------------------------------------------------------------------
 def _loss(x, logits):
-    b = x.shape[0]
-    l = torch.nn.functional.binary_cross_entropy_with_logits(logits.reshape(b, -1), x.reshape(b, -1), reduction="none")
-    return l.sum(dim=1).mean()
+    """The recipes' loss through the fused B200 kernel (checked against torch's BCE in test_recipe_loss_kernel)."""
+    from pytorch_generative_b200 import losses
+
+    return losses.bce_with_logits_sum_mean(logits, x)
+
+
+def test_recipe_loss_kernel(pg):
+    from pytorch_generative_b200 import losses
+
+    g = torch.Generator().manual_seed(5)
+    logits = (torch.randn(6, 3, 16, 16, generator=g) * 3).to(dev()).requires_grad_(True)
+    x = torch.rand(6, 3, 16, 16, generator=g).to(dev())
+    loss = losses.bce_with_logits_sum_mean(logits, x)
+    (loss * 1.7).backward()
+    lr = logits.detach().clone().requires_grad_(True)
+    ref = torch.nn.functional.binary_cross_entropy_with_logits(lr.reshape(6, -1), x.reshape(6, -1), reduction="none").sum(1).mean()
+    (ref * 1.7).backward()
+    assert abs(loss.item() - ref.item()) <= 1e-5 * abs(ref.item())
+    check("dlogits", logits.grad, lr.grad, 1e-5)
 
 
 def _build(pg, cls, cfg, state, sample_fn=None):
