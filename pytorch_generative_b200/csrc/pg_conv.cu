@@ -122,35 +122,53 @@ conv_small_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ d
   }
 }
 
-// dgrad w.r.t. the input image: dx[n,ci,y,x] = sum_{co,i,j} dy[(y-i+ph, x-j+pw), co] * w[co,ci,i,j].
-// One warp per input pixel, lanes over output channels.
+// dgrad w.r.t. the input image: dx[n,ci,y,x] = act'(x) * sum_{co,i,j} dy[(y-i+ph, x-j+pw), co] * w[co,ci,i,j].
+// The weight is staged once per block in shared memory as [tap][ci][co] (co contiguous: conflict-free, coalesced with
+// the dy rows); one warp per input pixel, lanes over output channels.
 __global__ void __launch_bounds__(256)
 conv_small_dgrad_kernel(const float* __restrict__ w, const float* __restrict__ dy, const ConvArgs a,
                         const float* __restrict__ x, float* __restrict__ dx) {
+  extern __shared__ float wt[];  // [kh*kw][Cin][Cout]
+  const int taps = a.kh * a.kw;
+  for (int t = threadIdx.x; t < taps * a.Cin * a.Cout; t += blockDim.x) {
+    const int co = t % a.Cout, ci = (t / a.Cout) % a.Cin, tap = t / (a.Cout * a.Cin);
+    wt[t] = w[((size_t)co * a.Cin + ci) * taps + tap];
+  }
+  __syncthreads();
   const int lane = threadIdx.x & 31;
-  const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int HW = a.H * a.W;
   const long long P = (long long)a.N * HW;
-  if (gw >= P) return;
-  const int n = (int)(gw / HW), rem = (int)(gw % HW);
-  const int y = rem / a.W, xx = rem % a.W;
-  for (int ci = 0; ci < a.Cin; ++ci) {
-    float acc = 0.f;
-    for (int i = 0; i < a.kh; ++i) {
-      const int yo = y - i + a.ph;
-      if (yo < 0 || yo >= a.H) continue;
-      for (int j = 0; j < a.kw; ++j) {
-        const int xo = xx - j + a.pw;
-        if (xo < 0 || xo >= a.W) continue;
-        const float* dyr = dy + ((size_t)n * HW + (size_t)yo * a.W + xo) * a.Cout;
-        for (int co = lane; co < a.Cout; co += 32)
-          acc = fmaf(dyr[co], __ldg(w + (((size_t)co * a.Cin + ci) * a.kh + i) * a.kw + j), acc);
+  const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; gw < P; gw += warps) {
+    const int n = (int)(gw / HW), rem = (int)(gw % HW);
+    const int y = rem / a.W, xx = rem % a.W;
+    for (int c0 = 0; c0 < a.Cin; c0 += 4) {  // input channels in groups of 4 accumulators
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int i = 0; i < a.kh; ++i) {
+        const int yo = y - i + a.ph;
+        if (yo < 0 || yo >= a.H) continue;
+        for (int j = 0; j < a.kw; ++j) {
+          const int xo = xx - j + a.pw;
+          if (xo < 0 || xo >= a.W) continue;
+          const float* dyr = dy + ((size_t)n * HW + (size_t)yo * a.W + xo) * a.Cout;
+          const float* wr = wt + ((size_t)(i * a.kw + j) * a.Cin + c0) * a.Cout;
+          for (int co = lane; co < a.Cout; co += 32) {
+            const float d = dyr[co];
+#pragma unroll
+            for (int ci = 0; ci < 4; ++ci)
+              if (c0 + ci < a.Cin) acc[ci] = fmaf(d, wr[ci * a.Cout + co], acc[ci]);
+          }
+        }
       }
-    }
-    acc = warp_sum(acc);
-    if (lane == 0) {
-      const size_t off = (((size_t)n * a.Cin + ci) * a.H + y) * a.W + xx;
-      dx[off] = a.pre_act == PG_ACT_NONE ? acc : acc * pg_act_bwd(a.pre_act, x[off]);
+#pragma unroll
+      for (int ci = 0; ci < 4; ++ci) {
+        if (c0 + ci >= a.Cin) break;
+        const float v = warp_sum(acc[ci]);
+        if (lane == 0) {
+          const size_t off = (((size_t)n * a.Cin + c0 + ci) * a.H + y) * a.W + xx;
+          dx[off] = a.pre_act == PG_ACT_NONE ? v : v * pg_act_bwd(a.pre_act, x[off]);
+        }
+      }
     }
   }
 }
@@ -296,8 +314,13 @@ extern "C" int pg_conv_small_bwd(const float* x_nchw, const float* w_oihw, const
     if (pg_colsum_f32(dy_pm, Cout, (int)P, Cout, dbias, 1, stream_)) return 1;
   }
   if (dx_nchw) {
-    const long long threads = P * 32;
-    conv_small_dgrad_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(w_oihw, dy_pm, a, x_nchw, dx_nchw);
+    const size_t smem_w = (size_t)a.K * Cout * sizeof(float);
+    PG_REQUIRE(smem_w <= 200 * 1024, "pg_conv_small_bwd: weight tile %zu B too large for shared memory", smem_w);
+    PG_CUDA(cudaFuncSetAttribute(conv_small_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    long long blocks = (P * 32 + 255) / 256;
+    const long long cap = (long long)pg_num_sms() * 4;
+    if (blocks > cap) blocks = cap;
+    conv_small_dgrad_kernel<<<(unsigned)blocks, 256, smem_w, stream>>>(w_oihw, dy_pm, a, x_nchw, dx_nchw);
     if (pg_check_launch("pg_conv_small_bwd(dgrad)")) return 1;
   }
   return 0;

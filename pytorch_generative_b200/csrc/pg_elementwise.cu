@@ -151,8 +151,20 @@ ln_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x, const f
   for (int row = warp_global; row < P; row += num_warps) {
     const float mean = __ldg(mean_in + row);
     const float rstd = __ldg(rstd_in + row);
-    float4 xh[V], gy[V];
+    float4 xh[V], gy[V], rsum[V];
     float s1 = 0.f, s2 = 0.f;
+    // residual-gradient tiles are fetched up front so that every load of this row is in flight before the
+    // (serial) warp reductions below
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const size_t off = (size_t)row * C / 4 + i * 32 + lane;
+      rsum[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (dres0) rsum[i] = __ldcs(reinterpret_cast<const float4*>(dres0) + off);
+      if (dres1) {
+        const float4 r = __ldcs(reinterpret_cast<const float4*>(dres1) + off);
+        rsum[i].x += r.x; rsum[i].y += r.y; rsum[i].z += r.z; rsum[i].w += r.w;
+      }
+    }
 #pragma unroll
     for (int i = 0; i < V; ++i) {
       const float4 xv = __ldcs(reinterpret_cast<const float4*>(x + (size_t)row * C) + i * 32 + lane);
@@ -183,14 +195,7 @@ ln_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x, const f
       o.z = rstd * (gy[i].z - m1 - xh[i].z * m2);
       o.w = rstd * (gy[i].w - m1 - xh[i].w * m2);
       const size_t off = (size_t)row * C / 4 + i * 32 + lane;
-      if (dres0) {
-        const float4 r = __ldcs(reinterpret_cast<const float4*>(dres0) + off);
-        o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
-      }
-      if (dres1) {
-        const float4 r = __ldcs(reinterpret_cast<const float4*>(dres1) + off);
-        o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
-      }
+      o.x += rsum[i].x; o.y += rsum[i].y; o.z += rsum[i].z; o.w += rsum[i].w;
       ds[i].x += o.x; ds[i].y += o.y; ds[i].z += o.z; ds[i].w += o.w;
       if (dx_f32) __stcs(reinterpret_cast<float4*>(dx_f32) + off, o);
       if (dx_bf16) reinterpret_cast<uint2*>(dx_bf16)[off] = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));

@@ -624,23 +624,29 @@ int dispatch_bn(const void* A, int64_t lda, const void* B, int64_t ldb, GemmPara
   else bn = 32;
   if (B_MN && bn < 64) bn = 64;  // MN-major operands are staged in 64-wide swizzle atoms
   const pg_gemm_epilogue& e = p.epi;
+  const int epi = (e.res0 ? SLAB_F32 : 0) + (e.res1 ? SLAB_F32 : 0) + (e.dact != PG_ACT_NONE ? SLAB_BF16 : 0) +
+                  (e.out_f32 ? SLAB_F32 : 0) + (e.out_pre ? SLAB_BF16 : 0) + (e.out_bf16 ? SLAB_BF16 : 0);
+  const bool pure_acc = e.accumulate && !e.bias && !e.res0 && !e.res1;
+  const bool staged = p.vec_ok && (!e.accumulate || pure_acc);
+  if constexpr (!A_MN) {
+    // CTA pairs (cta_group::2, 256 x 256 tiles) for the big pixel-major GEMMs (forward / dgrad): enough tiles to fill
+    // 74 pairs, and room for >= 3 operand stages of 32 KB next to the epilogue slabs.
+    static const bool no_pairs = getenv("PG_GEMM_NO_PAIRS") != nullptr;
+    const int tiles = ((p.M + 255) / 256) * ((p.N + 255) / 256);
+    const bool fits = !staged || (SMEM_LIMIT - 2 * epi - 1536) / (A_STAGE_BYTES + 128 * BK * 2) >= 3;
+    if (!no_pairs && bn == 256 && p.splits == 1 && tiles >= pg_num_sms() / 2 && fits) {
+      p.num_n_blk = (p.N + 255) / 256;
+      return launch_tc<256, false, B_MN, true>(A, lda, B, ldb, p, stream);
+    }
+  }
   if (bn == 256) {
     // fp32-heavy staged epilogues (residual stream in/out) need more slab space than a 256-wide tile leaves
     // next to a >= 3-deep operand pipeline; those GEMMs are HBM-bound anyway, so take the 128-wide tile.
-    const int epi = (e.res0 ? SLAB_F32 : 0) + (e.res1 ? SLAB_F32 : 0) + (e.dact != PG_ACT_NONE ? SLAB_BF16 : 0) +
-                    (e.out_f32 ? SLAB_F32 : 0) + (e.out_pre ? SLAB_BF16 : 0) + (e.out_bf16 ? SLAB_BF16 : 0);
-    const bool staged = p.vec_ok && (!e.accumulate || (!e.bias && !e.res0 && !e.res1)) ;
     if (staged && (SMEM_LIMIT - 2 * epi - 1536) / (A_STAGE_BYTES + 256 * BK * 2) < 3) bn = 128;
     // Narrow problems with few tiles prefer 128 to spread over more SMs.
     if (bn == 256 && ((p.M + BM - 1) / BM) * ((p.N + 255) / 256) * p.splits < pg_num_sms() && p.N % 256 != 0) bn = 128;
   }
   p.num_n_blk = (p.N + bn - 1) / bn;
-  if constexpr (!A_MN) {
-    // CTA pairs for the big pixel-major GEMMs (forward / dgrad): 256 x 256 tiles, enough of them to fill 74 pairs
-    static const bool no_pairs = getenv("PG_GEMM_NO_PAIRS") != nullptr;
-    if (!no_pairs && bn == 256 && p.splits == 1 && ((p.M + 255) / 256) * p.num_n_blk >= pg_num_sms() / 2)
-      return launch_tc<256, false, B_MN, true>(A, lda, B, ldb, p, stream);
-  }
   switch (bn) {
     case 256: return launch_tc<256, A_MN, B_MN>(A, lda, B, ldb, p, stream);
     case 128: return launch_tc<128, A_MN, B_MN>(A, lda, B, ldb, p, stream);

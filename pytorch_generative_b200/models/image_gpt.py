@@ -128,6 +128,17 @@ class _ImageGPTStack(torch.autograd.Function):
                                                                     sv["rstd_f"], want_colsum=True)
         del daf
 
+        # one zero-filled fp32 arena for every weight gradient of the stack (the wgrad GEMMs accumulate into it with
+        # TMA reduce-adds): a single memset instead of four per block
+        qkv_rows = sv["blocks"][0]["wqkv"].shape[0] if n_blocks else 0
+        dvs = sv["blocks"][0]["meta"]["dv_slot"] if n_blocks else 0
+        per_block = 4 * C * C + 4 * C * C + C * H * dvs + qkv_rows * C
+        arena = torch.zeros(n_blocks * per_block, dtype=F32, device=dev)
+
+        def carve(b, off, rows, cols):
+            start = b * per_block + off
+            return arena[start: start + rows * cols].view(rows, cols)
+
         for b in reversed(range(n_blocks)):
             blk = sv["blocks"][b]
             base_i = 3 + b * PARAMS_PER_BLOCK
@@ -135,12 +146,12 @@ class _ImageGPTStack(torch.autograd.Function):
             meta, dv_slot = blk["meta"], blk["meta"]["dv_slot"]
             # x_new = x + h + fc2(gelu(fc1(ln2(h))))
             grads[base_i + 13] = dx_sum
-            dw2 = torch.zeros(C, 4 * C, dtype=F32, device=dev)
+            dw2 = carve(b, 0, C, 4 * C)
             ops.linear_wgrad(dx_b, blk["g"], dw2)
             grads[base_i + 12] = dw2.view(C, 4 * C, 1, 1)
             du = ops.linear_dgrad(dx_b, blk["w2"], aux=blk["u"], dact=L.ACT_GELU)
             grads[base_i + 11] = ops.bias_grad(du)
-            dw1 = torch.zeros(4 * C, C, dtype=F32, device=dev)
+            dw1 = carve(b, 4 * C * C, 4 * C, C)
             ops.linear_wgrad(du, blk["a2"], dw1)
             grads[base_i + 10] = dw1.view(4 * C, C, 1, 1)
             da2 = ops.linear_dgrad(du, blk["w1"])
@@ -150,7 +161,7 @@ class _ImageGPTStack(torch.autograd.Function):
                 da2, blk["h"], ln2_w.detach(), blk["mean2"], blk["rstd2"], dres0=dx, want_colsum=True)
             del da2
             # h = x + proj(attn)
-            dwp = torch.zeros(C, H * dv_slot, dtype=F32, device=dev)
+            dwp = carve(b, 8 * C * C, C, H * dv_slot)
             ops.linear_wgrad(dh_b, blk["o"], dwp)
             grads[base_i + 6] = (dwp if meta["identity"] else dwp[:, blk["cols_v"]]).reshape(C, C, 1, 1)
             do = ops.linear_dgrad(dh_b, blk["wp"])
@@ -161,7 +172,7 @@ class _ImageGPTStack(torch.autograd.Function):
                          dqkv[:, 2 * H * slot:], n, S, H, meta["dk"], dv_slot, False)
             del do
             dbqkv = ops.bias_grad(dqkv)
-            dwqkv = torch.zeros(blk["wqkv"].shape, dtype=F32, device=dev)
+            dwqkv = carve(b, 8 * C * C + C * H * dv_slot, qkv_rows, C)
             ops.linear_wgrad(dqkv, blk["a1"], dwqkv)
             if meta["identity"]:  # heads fill their slots: plain slices of the fused gradient buffers
                 grads[base_i + 2] = dwqkv[:C].view(C, C, 1, 1)
