@@ -30,15 +30,28 @@ sys.path.insert(0, ROOT)
 
 CONFIGS = {
     # BASELINE.json configs[4] — the configuration the metric is quoted on (fits one GPU)
-    "c5": dict(name="ImageGPT 3x32x32 CIFAR-10-shaped, 24 blocks / 8 heads / 512 ch",
+    "c5": dict(name="ImageGPT 3x32x32 CIFAR-10-shaped, 24 blocks / 8 heads / 512 ch", cls="ImageGPT", oracle="image_gpt",
                cfg=dict(in_channels=3, out_channels=3, in_size=32, n_transformer_blocks=24, n_attention_heads=8,
                         n_embedding_channels=512),
                shape=(3, 32, 32), batch=64, lr=5e-3, algo_gflop_per_img=541.289, cpu_batch=1),
     # BASELINE.json configs[1]
-    "c2": dict(name="ImageGPT 1x28x28 MNIST-shaped, 8 blocks / 4 heads / 64 ch",
+    "c2": dict(name="ImageGPT 1x28x28 MNIST-shaped, 8 blocks / 4 heads / 64 ch", cls="ImageGPT", oracle="image_gpt",
                cfg=dict(in_channels=1, out_channels=1, in_size=28, n_transformer_blocks=8, n_attention_heads=4,
                         n_embedding_channels=64),
                shape=(1, 28, 28), batch=64, lr=5e-3, algo_gflop_per_img=3.742, cpu_batch=16),
+    # the other BASELINE.json configs (secondary numbers, `--config cN`; the conv models compose the drop-in modules)
+    "c1": dict(name="PixelCNN 1x28x28 binarized-MNIST-shaped, 15 residual / 16 ch", cls="PixelCNN", oracle="pixel_cnn",
+               cfg=dict(in_channels=1, out_channels=1, n_residual=15, residual_channels=16, head_channels=32),
+               shape=(1, 28, 28), batch=16, lr=1e-3, algo_gflop_per_img=0.171, cpu_batch=16),
+    "c3": dict(name="GatedPixelCNN 3x32x32 CIFAR-10-shaped, 15 gated layers / 128 ch", cls="GatedPixelCNN",
+               oracle="gated_pixel_cnn",
+               cfg=dict(in_channels=3, out_channels=3, n_gated=15, gated_channels=128, head_channels=32),
+               shape=(3, 32, 32), batch=128, lr=1e-3, algo_gflop_per_img=30.164, cpu_batch=8),
+    "c4": dict(name="PixelSNAIL 3x32x32 CIFAR-10-shaped, 8 blocks / 256 ch, key 16 / value 128", cls="PixelSNAIL",
+               oracle="pixel_snail",
+               cfg=dict(in_channels=3, out_channels=3, n_channels=256, n_pixel_snail_blocks=8, n_residual_blocks=2,
+                        attention_key_channels=16, attention_value_channels=128),
+               shape=(3, 32, 32), batch=128, lr=1e-3, algo_gflop_per_img=92.061, cpu_batch=4),
 }
 
 
@@ -134,7 +147,7 @@ def run_ours(args):
 
     batch = args.batch or spec["batch"]
     torch.manual_seed(0)
-    model = models.ImageGPT(**spec["cfg"]).to(dev)
+    model = getattr(models, spec["cls"])(**spec["cfg"]).to(dev)
     train_model = model
     parallel.broadcast_parameters(model)       # rank 0's weights everywhere (what DDP does at construction)
     params = [p for p in model.parameters()]
@@ -190,6 +203,16 @@ def run_ours(args):
     gemm_ms = sum(a.elapsed_time(b) for _, a, b in gemm_events)
     gemm_flops = sum(f for f, _, _ in gemm_events)
 
+    sample_ms = None
+    if args.sample and rank == 0:
+        # sample() latency (reference trainer.py:212-220 draws n=16): raster scan through the public API, wall clock
+        model.eval()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        model.sample(n_samples=16)
+        torch.cuda.synchronize()
+        sample_ms = (time.perf_counter() - t0) * 1e3
+
     # ---- end-to-end: pinned host batch -> H2D -> step -> D2H scalars, through the Module API ----
     def e2e_step():
         return step(x_host.to(dev, non_blocking=True))
@@ -209,7 +232,8 @@ def run_ours(args):
     achieved_tf = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
     n_gemm = len(gemm_events)
     out = {
-        "metric": "images/sec training step (ImageGPT CIFAR-10 32x32)", "value": round(value, 2), "unit": "images/sec",
+        "metric": "images/sec training step (ImageGPT CIFAR-10 32x32)" if args.config == "c5" else
+        f"images/sec training step ({spec['name']})", "value": round(value, 2), "unit": "images/sec",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": spec["name"] + f", per-GPU batch {batch}, Adam lr {spec['lr']}, fp32 master weights, "
@@ -228,6 +252,9 @@ def run_ours(args):
                      "step_frac_of_peak": round(spec["algo_gflop_per_img"] * value / world / 1e3 / pk["tf_sustained"], 4)},
         "last_loss": last[0], "last_grad_norm": last[1],
     }
+    if sample_ms is not None:
+        out["sample"] = {"n_samples": 16, "pixels": spec["shape"][1] * spec["shape"][2], "ms": round(sample_ms, 1),
+                         "method": "reference semantics: one full forward per pixel (base.py:97-120)"}
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(spec, steps=2, warmup=1)
     print(json.dumps(out), flush=True)
@@ -245,7 +272,7 @@ def _oracle_state(spec):
     from pytorch_generative_b200 import models
 
     torch.manual_seed(0)
-    m = models.ImageGPT(**spec["cfg"])
+    m = getattr(models, spec["cls"])(**spec["cfg"])
     return {k: v.detach().clone() for k, v in m.state_dict().items()}
 
 
@@ -262,7 +289,7 @@ def cpu_baseline(spec, steps, warmup, budget_s=45.0):
     threads = max(1, min(avail, 32))
     torch.set_num_threads(threads)
     nb = spec["cpu_batch"]
-    ts = O.TrainState("image_gpt", _oracle_state(spec), spec["cfg"], lr=spec["lr"])
+    ts = O.TrainState(spec["oracle"], _oracle_state(spec), spec["cfg"], lr=spec["lr"])
     x = synthetic_batch(nb, spec["shape"], seed=0)
     times, t_start = [], time.perf_counter()
     for i in range(warmup + steps):
@@ -308,6 +335,7 @@ def main():
     ap.add_argument("--config", default="c5", choices=sorted(CONFIGS))
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the recipe's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sample", action="store_true", help="also time model.sample(n_samples=16)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
