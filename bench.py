@@ -80,6 +80,14 @@ def peaks():
     return dict(hbm_gbs=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback (B200_PROFILING.md)")
 
 
+def measured_traffic():
+    """DRAM bytes per GEMM launch from the committed ncu capture (None when the profile is absent)."""
+    path = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
+    if not os.path.exists(path):
+        return None
+    return round(json.load(open(path))["traffic_bytes_per_launch"])
+
+
 class ClockSampler:
     """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
 
@@ -194,14 +202,15 @@ def run_ours(args):
 
     # ---- device-resident timing, with per-GEMM CUDA events for the roofline line ----
     gemm_events = []
-    L.gemm_timing_hook = lambda flops, a, b: gemm_events.append((flops, a, b))
+    L.gemm_timing_hook = lambda flops, a, b, io: gemm_events.append((flops, a, b, io))
     launches0 = L.launch_count()
     with ClockSampler(local_rank) as clocks:
         ms_total, last = timed(lambda: step(x_dev), args.steps)
     launches = L.launch_count() - launches0
     L.gemm_timing_hook = None
-    gemm_ms = sum(a.elapsed_time(b) for _, a, b in gemm_events)
-    gemm_flops = sum(f for f, _, _ in gemm_events)
+    gemm_ms = sum(a.elapsed_time(b) for _, a, b, _ in gemm_events)
+    gemm_flops = sum(f for f, _, _, _ in gemm_events)
+    gemm_bytes = sum(io for _, _, _, io in gemm_events)
 
     sample_ms = None
     if args.sample and rank == 0:
@@ -246,7 +255,10 @@ def run_ours(args):
         "clocks": clocks.summary(),
         "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (pg_gemm_bf16, tcgen05 1x1-conv fwd/dgrad/wgrad)",
                      "achieved": round(achieved_tf, 1), "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-                     "frac": round(achieved_tf / pk["tf_sustained"], 4), "traffic": None,
+                     "frac": round(achieved_tf / pk["tf_sustained"], 4), "traffic": measured_traffic(),
+                     "traffic_unit": "DRAM bytes per launch (ncu dram__bytes_read+write, profiles/r01_gemm_traffic.json)",
+                     "algo_bytes_per_launch": round(gemm_bytes / max(n_gemm, 1)),
+                     "flops_per_launch": round(gemm_flops / max(n_gemm, 1)),
                      "launches_timed": n_gemm, "share_of_step": round(gemm_ms / ms_total, 4), "peak_source": pk["source"],
                      "step_algo_tflops": round(spec["algo_gflop_per_img"] * value / world / 1e3, 1),
                      "step_frac_of_peak": round(spec["algo_gflop_per_img"] * value / world / 1e3 / pk["tf_sustained"], 4)},

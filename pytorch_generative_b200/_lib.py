@@ -118,7 +118,7 @@ def launch_count():
 
 
 # Optional per-call timing hook used by bench.py: when set, gemm() brackets its launch with CUDA events on
-# the launching stream and reports (flops, start_event, end_event).
+# the launching stream and reports (flops, start_event, end_event, algorithmic_bytes).
 gemm_timing_hook = None
 
 _sm_count = None
@@ -174,7 +174,9 @@ def gemm(A, B, M, N, K, *, a_mn=False, b_mn=False, bias=None, aux=None, dact=ACT
                             _stream()), "pg_gemm_bf16")
     if hook is not None:
         ev1.record()
-        hook(2.0 * M * N * K, ev0, ev1)
+        io = 2 * (M * K + N * K) + M * N * (2 * (out_bf16 is not None) + 2 * (out_pre is not None) + 4 * (out_f32 is not None)
+                                            + 2 * (aux is not None) + 4 * (res0 is not None) + 4 * (res1 is not None))
+        hook(2.0 * M * N * K, ev0, ev1, io)
 
 
 def colsum(x, out, accumulate=False):
