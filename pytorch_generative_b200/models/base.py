@@ -64,6 +64,11 @@ class AutoregressiveModel(GenerativeModel):
         shape = (n_samples, int(self._c), int(self._h), int(self._w))
         return torch.full(shape, -1.0, device=self.device)
 
+    # Models whose forward is exactly row-causal (the logits of image row r depend on rows <= r only, and every
+    # kernel computes an output row from the same operands in the same order whatever the image height) can evaluate
+    # a pixel on the top (r + 1) rows of the canvas: bit-identical logits for roughly half the work on average.
+    _row_truncated_sampling = True
+
     @torch.no_grad()
     def sample(self, n_samples=None, conditioned_on=None):
         """Generates samples pixel by pixel; entries of `conditioned_on` that are >= 0 are kept."""
@@ -71,7 +76,8 @@ class AutoregressiveModel(GenerativeModel):
         n, c, h, w = canvas.shape
         for row in range(h):
             for col in range(w):
-                logits = self.forward(canvas)[:, :, row, col]
+                visible = canvas[:, :, : row + 1] if self._row_truncated_sampling else canvas
+                logits = self.forward(visible)[:, :, row, col]
                 drawn = self._sample_fn(logits).view(n, c)
                 current = canvas[:, :, row, col]
                 canvas[:, :, row, col] = torch.where(current < 0, drawn, current)

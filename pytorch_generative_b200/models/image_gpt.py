@@ -61,7 +61,7 @@ class _ImageGPTStack(torch.autograd.Function):
         C = in_w.shape[0]
         keep = any(ctx.needs_input_grad)
 
-        x_in = (x + pos).contiguous()
+        x_in = (x + pos[:, :, : h, : w]).contiguous()  # sampling evaluates the top rows of the canvas only
         xs = torch.empty(P, C, dtype=F32, device=x.device)
         L.conv_small_fwd(x_in, in_w.detach().contiguous(), in_b.detach(), (in_w.shape[2] // 2, in_w.shape[3] // 2),
                          out_f32=xs)
@@ -200,7 +200,9 @@ class _ImageGPTStack(torch.autograd.Function):
         L.conv_small_bwd(sv["x_in"], in_w.detach().contiguous(), dx, (in_w.shape[2] // 2, in_w.shape[3] // 2), dw=dw_in,
                          dbias=None, dx=dx_in)
         grads[1], grads[2] = dw_in, db_in
-        grads[0] = dx_in.sum(dim=0, keepdim=True)
+        dpos = torch.zeros_like(params[0])
+        dpos[:, :, : h, : w] = dx_in.sum(dim=0, keepdim=True)
+        grads[0] = dpos
         ctx.saved = None
         return (dx_in if ctx.needs_input_grad[0] else None, None, None, *grads)
 

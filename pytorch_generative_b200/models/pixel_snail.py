@@ -68,6 +68,10 @@ class PixelSNAILBlock(nn.Module):
 class PixelSNAIL(base.AutoregressiveModel):
     """The PixelSNAIL model — constructor of reference pixel_snail.py:130-180."""
 
+    # the positional encoding is a function of the image height (arange(-.5, .5, 1/h)), so a pixel cannot be evaluated
+    # on a truncated canvas: sample() runs the full forward per pixel, exactly like the reference
+    _row_truncated_sampling = False
+
     def __init__(self, in_channels=1, out_channels=1, n_channels=64, n_pixel_snail_blocks=8, n_residual_blocks=2,
                  attention_key_channels=4, attention_value_channels=32, sample_fn=None):
         super().__init__(sample_fn)

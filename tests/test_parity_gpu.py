@@ -332,3 +332,18 @@ def test_wide_causal_conv2d_matches_oracle(pg):
         check("wide conv dw", m.weight.grad, gw, TOL_BF16)
         check("wide conv db", m.bias.grad, gb, TOL_BF16)
         assert (m.weight.grad.cpu() * (1 - m.mask.cpu())).abs().sum() > 0  # masked taps receive gradient (dense wgrad)
+
+
+@pytest.mark.parametrize("name", ["image_gpt", "pixel_cnn", "gated_pixel_cnn"])
+def test_row_truncated_forward_is_bit_identical(pg, name):
+    """sample() evaluates pixel (r, c) on the top r+1 rows of the canvas: the logits of those rows must be bit-for-bit
+    the ones of the full forward (row causality + row-independent kernels), so the sampling order/values are unchanged."""
+    fx = load(f"model_{name}.pt")
+    m = _build(pg, fx["cls"], fx["cfg"], fx["state_before"]).eval()
+    assert m._row_truncated_sampling
+    x = fx["x"].to(dev())
+    with torch.no_grad():
+        full = m(x)
+        for r in (0, 3, 6):
+            part = m(x[:, :, : r + 1].contiguous())
+            assert torch.equal(part, full[:, :, : r + 1]), (name, r)
