@@ -69,15 +69,51 @@ class AutoregressiveModel(GenerativeModel):
     # a pixel on the top (r + 1) rows of the canvas: bit-identical logits for roughly half the work on average.
     _row_truncated_sampling = True
 
+    # sample() replays one CUDA graph per distinct forward shape (one per image row when row-truncated, one in total
+    # otherwise): a per-pixel forward of a small batch is ~700 tiny launches, i.e. host-bound when launched eagerly.
+    _sample_with_graphs = True
+
+    def _pixel_logits_fn(self, canvas, rows):
+        """Returns a callable computing forward(canvas[:, :, :rows]) (eager, or a captured-graph replay)."""
+        n, c, _, w = canvas.shape
+        if not (self._sample_with_graphs and canvas.is_cuda):
+            return lambda: self.forward(canvas[:, :, :rows])
+        cache = self.__dict__.setdefault("_sample_graphs", {})
+        key = (n, c, rows, w, str(canvas.device))
+        if key not in cache:
+            static_in = torch.empty(n, c, rows, w, dtype=canvas.dtype, device=canvas.device)
+            static_in.copy_(canvas[:, :, :rows])
+            try:
+                self.forward(static_in)  # warm-up outside capture (lazy one-time initialisation in the kernels' host code)
+                torch.cuda.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    static_out = self.forward(static_in)
+                cache[key] = (graph, static_in, static_out)
+            except RuntimeError:  # capture not possible in this context: launch eagerly (same kernels)
+                torch.cuda.synchronize()
+                cache[key] = None
+        entry = cache[key]
+        if entry is None:
+            return lambda: self.forward(canvas[:, :, :rows])
+        graph, static_in, static_out = entry
+
+        def run():
+            static_in.copy_(canvas[:, :, :rows])
+            graph.replay()
+            return static_out
+
+        return run
+
     @torch.no_grad()
     def sample(self, n_samples=None, conditioned_on=None):
         """Generates samples pixel by pixel; entries of `conditioned_on` that are >= 0 are kept."""
         canvas = self._start_canvas(n_samples, conditioned_on)
         n, c, h, w = canvas.shape
         for row in range(h):
+            logits_fn = self._pixel_logits_fn(canvas, row + 1 if self._row_truncated_sampling else h)
             for col in range(w):
-                visible = canvas[:, :, : row + 1] if self._row_truncated_sampling else canvas
-                logits = self.forward(visible)[:, :, row, col]
+                logits = logits_fn()[:, :, row, col]
                 drawn = self._sample_fn(logits).view(n, c)
                 current = canvas[:, :, row, col]
                 canvas[:, :, row, col] = torch.where(current < 0, drawn, current)
