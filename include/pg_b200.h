@@ -151,6 +151,14 @@ int pg_causal_attn_bwd(const void* q, int64_t ld_q, const void* k, int64_t ld_k,
                        void* dv_, int64_t ld_dv, int N, int S, int H, int dk, int dv, float scale, int strict,
                        int impl, void* stream);
 
+/* Incremental (KV-cached) attention for AutoregressiveModel.sample (reference models/base.py:97-120 recomputes the full
+ * forward per pixel; causality makes the per-position update exact): appends the current position's k / v rows
+ * ([N, H*d]) to the caches ([N*S, H*d]) at row *pos_dev and attends over cache rows [0, pos] ([0, pos) if strict).
+ * pos_dev is a device int so that one captured CUDA graph serves the whole raster scan. */
+int pg_attn_decode(const void* q, int64_t ld_q, const void* k_new, int64_t ld_kn, const void* v_new, int64_t ld_vn,
+                   void* k_cache, int64_t ld_kc, void* v_cache, int64_t ld_vc, void* o, int64_t ld_o,
+                   const int* pos_dev, int N, int S, int H, int dk, int dv, float scale, int strict, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Tap-list convolution for small channel counts (CausalConv2d input layers, Cin in {1,3}):
  * reference nn/convolution.py:41-43 (weight.data *= mask; F.conv2d).  x is NCHW fp32 (the model

@@ -52,6 +52,8 @@ _SIGNATURES = {
                            _vp, _i64, _i32, _i32, _i32, _i32, _i32, _f32, _i32, _i32, _vp],
     "pg_conv_small_fwd": [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp],
     "pg_conv_small_bwd": [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp],
+    "pg_attn_decode": [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i32, _i32, _i32, _i32, _i32,
+                       _f32, _i32, _vp],
     "pg_tap_gather": [_vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _vp],
     "pg_tap_scatter": [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _i64, _vp, _vp, _i64, _vp],
 }
@@ -336,3 +338,14 @@ def tap_scatter(dxcat, N, H, W, C, taps, act, x_pre, dx_f32=None, dx_bf16=None):
     _check(lib.pg_tap_scatter(_ptr(dxcat), N, H, W, C, len(taps), ctypes.cast(dy, ctypes.c_void_p),
                               ctypes.cast(dx, ctypes.c_void_p), act, pre_p, pre_ld, _ptr(dx_f32), _ptr(dx_bf16), ld_dx,
                               _stream()), "pg_tap_scatter")
+
+
+def attn_decode(q, k_new, v_new, k_cache, v_cache, o, pos_dev, N, S, H, dk, dv, strict, dk_true=None):
+    """One new position per image against the KV caches (see pg_attn_decode); pos_dev: int32 device scalar."""
+    lib = load()
+    (qp, ldq), (knp, ldkn), (vnp, ldvn) = _pm(q), _pm(k_new), _pm(v_new)
+    (kcp, ldkc), (vcp, ldvc), (op, ldo) = _pm(k_cache), _pm(v_cache), _pm(o)
+    assert pos_dev.dtype == torch.int32 and pos_dev.is_cuda
+    scale = 1.0 / math.sqrt(dk_true or dk)
+    _check(lib.pg_attn_decode(qp, ldq, knp, ldkn, vnp, ldvn, kcp, ldkc, vcp, ldvc, op, ldo, _ptr(pos_dev), N, S, H, dk, dv,
+                              scale, int(strict), _stream()), "pg_attn_decode")

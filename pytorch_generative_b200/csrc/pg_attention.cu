@@ -199,6 +199,67 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_simt(const AttnArgs a) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Incremental (KV-cached) attention for sampling: one new position per image.  One warp per (image, head):
+// appends this position's key / value rows to the caches, then attends over cache rows [0, pos] (or [0, pos) when
+// strict).  `pos` is read from device memory so that one captured CUDA graph serves every pixel of the raster scan.
+// ------------------------------------------------------------------------------------------------
+struct DecodeArgs {
+  const bf16 *q, *k_new, *v_new;   // [N, H*dk], [N, H*dk], [N, H*dv] rows of the current position
+  bf16 *k_cache, *v_cache;         // [N*S, H*dk], [N*S, H*dv]
+  bf16* out;                       // [N, H*dv]
+  int64_t ld_q, ld_kn, ld_vn, ld_kc, ld_vc, ld_o;
+  const int* pos;
+  int N, S, H, dk, dv, strict;
+  float scale;
+};
+
+__global__ void __launch_bounds__(128) attn_decode_kernel(const DecodeArgs a) {
+  extern __shared__ float sm[];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  float* sc = sm + w * (MAX_S + MAX_D);
+  float* qs = sc + MAX_S;
+  const int gw = blockIdx.x * 4 + w;
+  if (gw >= a.N * a.H) return;
+  const int n = gw / a.H, h = gw % a.H;
+  const int pos = *a.pos;
+  const size_t row0 = (size_t)n * a.S;
+  // append k, v of this position (visible to this warp's later reads through __syncwarp)
+  for (int d = lane; d < a.dk; d += 32) {
+    a.k_cache[(row0 + pos) * a.ld_kc + h * a.dk + d] = a.k_new[(size_t)n * a.ld_kn + h * a.dk + d];
+    qs[d] = __bfloat162float(a.q[(size_t)n * a.ld_q + h * a.dk + d]);
+  }
+  for (int d = lane; d < a.dv; d += 32)
+    a.v_cache[(row0 + pos) * a.ld_vc + h * a.dv + d] = a.v_new[(size_t)n * a.ld_vn + h * a.dv + d];
+  __syncwarp();
+  const int nkeys = a.strict ? pos : pos + 1;
+  float m = -INFINITY;
+  for (int j = lane; j < nkeys; j += 32) {
+    const bf16* kr = a.k_cache + (row0 + j) * a.ld_kc + h * a.dk;
+    float s = 0.f;
+    for (int d = 0; d < a.dk; ++d) s = fmaf(qs[d], __bfloat162float(kr[d]), s);
+    s *= a.scale;
+    sc[j] = s;
+    m = fmaxf(m, s);
+  }
+  m = warp_max(m);
+  float l = 0.f;
+  for (int j = lane; j < nkeys; j += 32) {
+    const float p = __expf(sc[j] - m);
+    sc[j] = p;
+    l += p;
+  }
+  l = warp_sum(l);
+  __syncwarp();
+  const float inv = nkeys > 0 ? 1.f / l : 0.f;
+  for (int d = lane; d < a.dv; d += 32) {
+    float acc = 0.f;
+    for (int j = 0; j < nkeys; ++j)
+      acc = fmaf(sc[j], __bfloat162float(a.v_cache[(row0 + j) * a.ld_vc + h * a.dv + d]), acc);
+    a.out[(size_t)n * a.ld_o + h * a.dv + d] = __float2bfloat16(acc * inv);
+  }
+}
+
 }  // namespace
 
 #include "pg_attention_tc.cuh"
@@ -263,4 +324,22 @@ extern "C" int pg_causal_attn_bwd(const void* q, int64_t ld_q, const void* k, in
     return pg_check_launch("pg_causal_attn_bwd(dkv simt)");
   }
   return attn_bwd_tc(a, stream);
+}
+
+extern "C" int pg_attn_decode(const void* q, int64_t ld_q, const void* k_new, int64_t ld_kn, const void* v_new, int64_t ld_vn,
+                              void* k_cache, int64_t ld_kc, void* v_cache, int64_t ld_vc, void* o, int64_t ld_o,
+                              const int* pos_dev, int N, int S, int H, int dk, int dv, float scale, int strict,
+                              void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  PG_REQUIRE(q && k_new && v_new && k_cache && v_cache && o && pos_dev, "pg_attn_decode: null argument");
+  PG_REQUIRE(S <= MAX_S && dk <= MAX_D && dv <= MAX_D, "pg_attn_decode: S<=%d, d<=%d", MAX_S, MAX_D);
+  DecodeArgs a;
+  a.q = (const bf16*)q; a.k_new = (const bf16*)k_new; a.v_new = (const bf16*)v_new;
+  a.k_cache = (bf16*)k_cache; a.v_cache = (bf16*)v_cache; a.out = (bf16*)o;
+  a.ld_q = ld_q; a.ld_kn = ld_kn; a.ld_vn = ld_vn; a.ld_kc = ld_kc; a.ld_vc = ld_vc; a.ld_o = ld_o;
+  a.pos = pos_dev; a.N = N; a.S = S; a.H = H; a.dk = dk; a.dv = dv; a.strict = strict; a.scale = scale;
+  const int warps = N * H;
+  const size_t smem = 4 * (MAX_S + MAX_D) * sizeof(float);
+  attn_decode_kernel<<<(warps + 3) / 4, 128, smem, stream>>>(a);
+  return pg_check_launch("pg_attn_decode");
 }

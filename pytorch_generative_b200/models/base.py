@@ -71,7 +71,7 @@ class AutoregressiveModel(GenerativeModel):
 
     # sample() replays one CUDA graph per distinct forward shape (one per image row when row-truncated, one in total
     # otherwise): a per-pixel forward of a small batch is ~700 tiny launches, i.e. host-bound when launched eagerly.
-    _sample_with_graphs = True
+    _sample_with_graphs = False  # opt-in: capture costs ~1 s per shape, worth it only for repeated sampling
 
     def _pixel_logits_fn(self, canvas, rows):
         """Returns a callable computing forward(canvas[:, :, :rows]) (eager, or a captured-graph replay)."""

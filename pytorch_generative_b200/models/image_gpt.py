@@ -226,6 +226,122 @@ class ImageGPT(base.AutoregressiveModel):
         if n_embedding_channels % 8 != 0:
             raise NotImplementedError("ImageGPT: n_embedding_channels must be a multiple of 8 on the B200 path")
 
+    # ------------------------------------------------------------------------------------------------------------
+    # Incremental sampling.  The reference's sample() (models/base.py:97-120) runs a full forward per pixel; the model is
+    # exactly causal, so the logits of pixel p only need p's own row through the stack plus the keys / values of the
+    # pixels before it.  Per pixel: input conv on the 3x3 window around p, and per block LN -> q|k|v GEMM (M = batch
+    # rows) -> pg_attn_decode over the K/V caches -> proj / MLP GEMMs with the same fused epilogues as training.  The
+    # step is captured once in a CUDA graph (the position lives in device memory) and replayed for every pixel; the
+    # raster order, the `sample_fn` hook and the "only entries < 0 are overwritten" rule are the base class's.
+    # ------------------------------------------------------------------------------------------------------------
+    _incremental_sampling = True
+
+    def _packed_weights(self):
+        C, H = self._input.weight.shape[0], self._n_heads
+        blocks = []
+        for blk in self._transformer:
+            (ln1_w, ln1_b, q_w, q_b, kv_w, kv_b, p_w, p_b, ln2_w, ln2_b, f1_w, f1_b, f2_w, f2_b) = blk.flat_params()
+            wq, bq, wkv, bkv, meta = pack_qkv_weights(q_w, q_b, kv_w, kv_b, H, C, C, C, C)
+            if meta["identity"]:
+                wp = ops.pack_weight(p_w)
+            else:
+                wp32 = torch.zeros(C, H * meta["dv_slot"], dtype=F32, device=p_w.device)
+                wp32[:, meta["rows_v"] - H * ops.HEAD_SLOT] = p_w.detach().reshape(C, -1)
+                wp = ops.to_bf16(wp32)
+            blocks.append(dict(wqkv=torch.cat((wq, wkv)), bqkv=torch.cat((bq, bkv)).contiguous(), wp=wp,
+                               w1=ops.pack_weight(f1_w), w2=ops.pack_weight(f2_w), dk=meta["dk"], dv_slot=meta["dv_slot"]))
+        return blocks, ops.pack_weight(self._out.weight)
+
+    def _sampler_step(self, st):
+        """One position for every image of the batch: st["patch"] (window of x + pos around the pixel) -> logits."""
+        n, C, H, S, eps = st["n"], st["C"], self._n_heads, st["S"], self._ln.eps
+        kh, kw = self._input.weight.shape[2:]
+        taps_out = torch.empty(n * kh * kw, C, dtype=F32, device=st["patch"].device)
+        L.conv_small_fwd(st["patch"], self._input.weight.detach().contiguous(), self._input.bias.detach(),
+                         (kh // 2, kw // 2), out_f32=taps_out)
+        xs = taps_out.view(n, kh * kw, C)[:, (kh // 2) * kw + kw // 2].contiguous()  # the window's centre pixel
+        slot = ops.HEAD_SLOT
+        for b, blk in enumerate(self._transformer):
+            wb = st["w"][b]
+            a1, _, _, _ = ops.layernorm_fwd(xs, blk._ln1.weight.detach(), blk._ln1.bias.detach(), eps)
+            qkv, _, _ = ops.linear_fwd(a1, wb["wqkv"], wb["bqkv"])
+            q, k, v = qkv[:, : H * slot], qkv[:, H * slot: 2 * H * slot], qkv[:, 2 * H * slot:]
+            o = torch.empty(n, H * wb["dv_slot"], dtype=BF16, device=xs.device)
+            L.attn_decode(q, k, v, st["kc"][b], st["vc"][b], o, st["pos"], n, S, H, slot, wb["dv_slot"], False,
+                          dk_true=wb["dk"])
+            _, _, hres = ops.linear_fwd(o, wb["wp"], blk._attn._proj.bias.detach(), res0=xs, want_bf16=False, want_f32=True)
+            a2, _, _, _ = ops.layernorm_fwd(hres, blk._ln2.weight.detach(), blk._ln2.bias.detach(), eps)
+            g, _, _ = ops.linear_fwd(a2, wb["w1"], blk._out[0].bias.detach(), act=L.ACT_GELU)
+            _, _, xs = ops.linear_fwd(g, wb["w2"], blk._out[2].bias.detach(), res0=xs, res1=hres, want_bf16=False,
+                                      want_f32=True)
+        af, _, _, _ = ops.layernorm_fwd(xs, self._ln.weight.detach(), self._ln.bias.detach(), eps)
+        _, _, logits = ops.linear_fwd(af, st["wo"], self._out.bias.detach(), want_bf16=False, want_f32=True)
+        return logits
+
+    def _sampler_state(self, n, c, h, w, device):
+        cache = self.__dict__.setdefault("_samplers", {})
+        key = (n, c, h, w, str(device))
+        blocks, wo = self._packed_weights()
+        st = cache.get(key)
+        if st is None:
+            C, H, S = self._input.weight.shape[0], self._n_heads, h * w
+            kh, kw = self._input.weight.shape[2:]
+            st = dict(n=n, C=C, S=S, w=blocks, wo=wo, graph=None,
+                      patch=torch.zeros(n, c, kh, kw, dtype=F32, device=device),
+                      pos=torch.zeros(1, dtype=torch.int32, device=device),
+                      kc=[torch.zeros(n * S, H * ops.HEAD_SLOT, dtype=BF16, device=device) for _ in blocks],
+                      vc=[torch.zeros(n * S, H * bw["dv_slot"], dtype=BF16, device=device) for bw in blocks])
+            cache[key] = st
+        else:  # refresh the packed weights in place: a captured graph keeps reading the same buffers
+            for old, new in zip(st["w"], blocks):
+                for k2 in ("wqkv", "bqkv", "wp", "w1", "w2"):
+                    old[k2].copy_(new[k2])
+            st["wo"].copy_(wo)
+        return st
+
+    @torch.no_grad()
+    def sample(self, n_samples=None, conditioned_on=None):
+        canvas = self._start_canvas(n_samples, conditioned_on)
+        n, c, h, w = canvas.shape
+        if not (self._incremental_sampling and canvas.is_cuda and h * w <= 1024 and h <= self._pos.shape[2]
+                and w <= self._pos.shape[3]):
+            return super().sample(conditioned_on=canvas)
+        self._input.weight.data *= self._input.mask
+        st = self._sampler_state(n, c, h, w, canvas.device)
+        kh, kw = self._input.weight.shape[2:]
+        ph, pw = kh // 2, kw // 2
+        xin = torch.zeros(n, c, h + 2 * ph, w + 2 * pw, dtype=F32, device=canvas.device)  # zero-padded (x + pos)
+        pos_emb = self._pos[:, :, :h, :w]
+        xin[:, :, ph: ph + h, pw: pw + w] = canvas + pos_emb
+        if st["graph"] is None:
+            st["patch"].copy_(xin[:, :, :kh, :kw])
+            st["pos"].fill_(0)
+            try:
+                self._sampler_step(st)  # warm-up outside capture
+                torch.cuda.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    st["logits"] = self._sampler_step(st)
+                st["graph"] = graph
+            except RuntimeError:
+                torch.cuda.synchronize()
+                st["graph"] = False  # capture unavailable here: launch the same step eagerly
+        for row in range(h):
+            for col in range(w):
+                st["patch"].copy_(xin[:, :, row: row + kh, col: col + kw])
+                st["pos"].fill_(row * w + col)
+                if st["graph"]:
+                    st["graph"].replay()
+                    logits = st["logits"]
+                else:
+                    logits = self._sampler_step(st)
+                drawn = self._sample_fn(logits).view(n, c)
+                current = canvas[:, :, row, col]
+                new = torch.where(current < 0, drawn, current)
+                canvas[:, :, row, col] = new
+                xin[:, :, row + ph, col + pw] = new + pos_emb[0, :, row, col]
+        return canvas
+
     def forward(self, x):
         if not x.is_cuda:
             raise RuntimeError("ImageGPT (B200 path) needs CUDA tensors; there is no CPU fallback")
