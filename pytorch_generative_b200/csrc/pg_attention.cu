@@ -214,50 +214,68 @@ struct DecodeArgs {
   float scale;
 };
 
+// One block (4 warps) per (image, head): the keys are split across the warps, partial (max, sum, output) are merged
+// through shared memory.
 __global__ void __launch_bounds__(128) attn_decode_kernel(const DecodeArgs a) {
-  extern __shared__ float sm[];
+  __shared__ float sc[MAX_S];
+  __shared__ float qs[MAX_D];
+  __shared__ float part_o[4][MAX_D];
+  __shared__ float part_m[4], part_l[4];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  float* sc = sm + w * (MAX_S + MAX_D);
-  float* qs = sc + MAX_S;
-  const int gw = blockIdx.x * 4 + w;
-  if (gw >= a.N * a.H) return;
-  const int n = gw / a.H, h = gw % a.H;
+  const int n = blockIdx.x / a.H, h = blockIdx.x % a.H;
   const int pos = *a.pos;
   const size_t row0 = (size_t)n * a.S;
-  // append k, v of this position (visible to this warp's later reads through __syncwarp)
-  for (int d = lane; d < a.dk; d += 32) {
+  for (int d = threadIdx.x; d < a.dk; d += 128) {
     a.k_cache[(row0 + pos) * a.ld_kc + h * a.dk + d] = a.k_new[(size_t)n * a.ld_kn + h * a.dk + d];
     qs[d] = __bfloat162float(a.q[(size_t)n * a.ld_q + h * a.dk + d]);
   }
-  for (int d = lane; d < a.dv; d += 32)
+  for (int d = threadIdx.x; d < a.dv; d += 128)
     a.v_cache[(row0 + pos) * a.ld_vc + h * a.dv + d] = a.v_new[(size_t)n * a.ld_vn + h * a.dv + d];
-  __syncwarp();
+  __syncthreads();
   const int nkeys = a.strict ? pos : pos + 1;
   float m = -INFINITY;
-  for (int j = lane; j < nkeys; j += 32) {
-    const bf16* kr = a.k_cache + (row0 + j) * a.ld_kc + h * a.dk;
+  for (int j = threadIdx.x; j < nkeys; j += 128) {
+    const uint4* kr = reinterpret_cast<const uint4*>(a.k_cache + (row0 + j) * a.ld_kc + h * a.dk);
     float s = 0.f;
-    for (int d = 0; d < a.dk; ++d) s = fmaf(qs[d], __bfloat162float(kr[d]), s);
+    for (int d8 = 0; d8 < a.dk / 8; ++d8) {
+      const uint4 kv = kr[d8];
+      const uint32_t kw[4] = {kv.x, kv.y, kv.z, kv.w};
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float2 f = unpack_bf16x2(kw[t]);
+        s = fmaf(qs[d8 * 8 + 2 * t], f.x, fmaf(qs[d8 * 8 + 2 * t + 1], f.y, s));
+      }
+    }
     s *= a.scale;
     sc[j] = s;
     m = fmaxf(m, s);
   }
   m = warp_max(m);
+  if (lane == 0) part_m[w] = m;
+  __syncthreads();
+  m = fmaxf(fmaxf(part_m[0], part_m[1]), fmaxf(part_m[2], part_m[3]));
   float l = 0.f;
-  for (int j = lane; j < nkeys; j += 32) {
+  for (int j = threadIdx.x; j < nkeys; j += 128) {
     const float p = __expf(sc[j] - m);
     sc[j] = p;
     l += p;
   }
   l = warp_sum(l);
-  __syncwarp();
+  if (lane == 0) part_l[w] = l;
+  __syncthreads();
+  l = (part_l[0] + part_l[1]) + (part_l[2] + part_l[3]);
   const float inv = nkeys > 0 ? 1.f / l : 0.f;
+  // PV: warp w takes keys w, w+4, ...; lanes over the value channels
   for (int d = lane; d < a.dv; d += 32) {
     float acc = 0.f;
-    for (int j = 0; j < nkeys; ++j)
+    for (int j = w; j < nkeys; j += 4)
       acc = fmaf(sc[j], __bfloat162float(a.v_cache[(row0 + j) * a.ld_vc + h * a.dv + d]), acc);
-    a.out[(size_t)n * a.ld_o + h * a.dv + d] = __float2bfloat16(acc * inv);
+    part_o[w][d] = acc;
   }
+  __syncthreads();
+  for (int d = threadIdx.x; d < a.dv; d += 128)
+    a.out[(size_t)n * a.ld_o + h * a.dv + d] =
+        __float2bfloat16(((part_o[0][d] + part_o[1][d]) + (part_o[2][d] + part_o[3][d])) * inv);
 }
 
 }  // namespace
@@ -338,8 +356,7 @@ extern "C" int pg_attn_decode(const void* q, int64_t ld_q, const void* k_new, in
   a.k_cache = (bf16*)k_cache; a.v_cache = (bf16*)v_cache; a.out = (bf16*)o;
   a.ld_q = ld_q; a.ld_kn = ld_kn; a.ld_vn = ld_vn; a.ld_kc = ld_kc; a.ld_vc = ld_vc; a.ld_o = ld_o;
   a.pos = pos_dev; a.N = N; a.S = S; a.H = H; a.dk = dk; a.dv = dv; a.strict = strict; a.scale = scale;
-  const int warps = N * H;
-  const size_t smem = 4 * (MAX_S + MAX_D) * sizeof(float);
-  attn_decode_kernel<<<(warps + 3) / 4, 128, smem, stream>>>(a);
+  PG_REQUIRE(dk % 8 == 0 && ld_kc % 8 == 0, "pg_attn_decode: dk and the cache pitch must be multiples of 8");
+  attn_decode_kernel<<<N * H, 128, 0, stream>>>(a);
   return pg_check_launch("pg_attn_decode");
 }

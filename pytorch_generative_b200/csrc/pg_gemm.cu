@@ -533,6 +533,70 @@ __global__ void gemm_simt_kernel(const bf16* __restrict__ A, int a_mn, int64_t l
   epilogue_row32(p, row, col0, ncols, true, accu);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Skinny forward GEMM (M <= 32 rows): the per-pixel step of incremental sampling multiplies a handful of rows (one per
+// image) by the full weight matrices.  A 128-row tensor-core tile would run on N/256 SMs and be latency-bound; here
+// every warp owns one output column, streams its weight row once (16-byte loads) against the A rows held in shared
+// memory, and the whole chip participates.  Same fused epilogue semantics (bias, residuals, activation).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+gemm_skinny_kernel(const bf16* __restrict__ A, int64_t lda, const bf16* __restrict__ B, int64_t ldb, const GemmParams p) {
+  extern __shared__ uint4 sA4[];  // [M][K/8] 16-byte units
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int K8 = p.K / 8;
+  for (int i = threadIdx.x; i < p.M * K8; i += blockDim.x)
+    sA4[i] = *reinterpret_cast<const uint4*>(A + (size_t)(i / K8) * lda + (i % K8) * 8);
+  __syncthreads();
+  const int n = blockIdx.x * 8 + warp;
+  if (n >= p.N) return;
+  float acc[32];
+#pragma unroll
+  for (int m = 0; m < 32; ++m) acc[m] = 0.f;
+  const uint4* wrow = reinterpret_cast<const uint4*>(B + (size_t)n * ldb);
+  for (int k8 = lane; k8 < K8; k8 += 32) {
+    const uint4 wv = __ldg(wrow + k8);
+    const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
+    float wf[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = unpack_bf16x2(ww[j]);
+      wf[2 * j] = f.x;
+      wf[2 * j + 1] = f.y;
+    }
+#pragma unroll
+    for (int m = 0; m < 32; ++m) {
+      if (m < p.M) {
+        const uint4 av = sA4[m * K8 + k8];
+        const uint32_t aw[4] = {av.x, av.y, av.z, av.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = unpack_bf16x2(aw[j]);
+          acc[m] = fmaf(f.x, wf[2 * j], fmaf(f.y, wf[2 * j + 1], acc[m]));
+        }
+      }
+    }
+  }
+  float mine = 0.f;
+#pragma unroll
+  for (int m = 0; m < 32; ++m) {
+    if (m < p.M) {
+      const float v = warp_sum(acc[m]);
+      if (lane == m) mine = v;
+    }
+  }
+  if (lane < p.M) {
+    const pg_gemm_epilogue& e = p.epi;
+    const int m = lane;
+    float t = mine * e.alpha;
+    if (e.bias) t += e.bias[n];
+    if (e.res0) t += e.res0[(size_t)m * e.ld_res + n];
+    if (e.res1) t += e.res1[(size_t)m * e.ld_res + n];
+    if (e.out_f32) e.out_f32[(size_t)m * e.ld_out_f32 + n] = t;
+    if (e.out_pre) reinterpret_cast<bf16*>(e.out_pre)[(size_t)m * e.ld_out_pre + n] = __float2bfloat16(t);
+    if (e.out_bf16) reinterpret_cast<bf16*>(e.out_bf16)[(size_t)m * e.ld_out_bf16 + n] = __float2bfloat16(pg_act_fwd(e.act, t));
+  }
+}
+
 template <int BN, bool A_MN, bool B_MN, bool TWO = false>
 int launch_tc(const void* A, int64_t lda, const void* B, int64_t ldb, GemmParams& p, cudaStream_t stream) {
   constexpr int B_ROWS = TWO ? BN / 2 : BN;
@@ -700,6 +764,15 @@ extern "C" int pg_gemm_bf16(const void* A, int a_mn_major, int64_t lda, const vo
     gemm_simt_kernel<<<(unsigned)blocks, threads, 0, stream>>>(reinterpret_cast<const bf16*>(A), a_mn_major, lda,
                                                                  reinterpret_cast<const bf16*>(B), b_mn_major, ldb, p);
     return pg_check_launch("pg_gemm_bf16(simt)");
+  }
+  if (!a_mn_major && !b_mn_major && M <= 32 && !epi->accumulate && epi->dact == PG_ACT_NONE && K % 8 == 0 &&
+      (reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0 &&
+      (size_t)M * K * 2 <= 160 * 1024) {
+    const size_t smem = (size_t)M * K * 2;
+    PG_CUDA(cudaFuncSetAttribute(gemm_skinny_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    gemm_skinny_kernel<<<(N + 7) / 8, 256, smem, stream>>>(reinterpret_cast<const bf16*>(A), lda,
+                                                           reinterpret_cast<const bf16*>(B), ldb, p);
+    return pg_check_launch("pg_gemm_bf16(skinny)");
   }
   if (!a_mn_major && !b_mn_major) return dispatch_bn<false, false>(A, lda, B, ldb, p, stream);
   if (!a_mn_major && b_mn_major) return dispatch_bn<false, true>(A, lda, B, ldb, p, stream);

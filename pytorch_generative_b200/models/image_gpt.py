@@ -323,9 +323,10 @@ class ImageGPT(base.AutoregressiveModel):
                 with torch.cuda.graph(graph):
                     st["logits"] = self._sampler_step(st)
                 st["graph"] = graph
-            except RuntimeError:
+            except RuntimeError as exc:
                 torch.cuda.synchronize()
                 st["graph"] = False  # capture unavailable here: launch the same step eagerly
+                st["graph_error"] = repr(exc)
         for row in range(h):
             for col in range(w):
                 st["patch"].copy_(xin[:, :, row: row + kh, col: col + kw])

@@ -167,6 +167,45 @@ def test_gemm_wgrad_splitk_accumulate(L, split_k):
     assert_close(f"wgrad split_k={split_k}", out, ref + 1.0, rtol=2e-5, atol=1e-3)
 
 
+@pytest.mark.parametrize("M,N,K", [(16, 2048, 512), (2, 96, 32), (32, 520, 2048), (5, 3, 64)])
+def test_gemm_skinny_rows(L, M, N, K):
+    """M <= 32 rows (the per-pixel step of incremental sampling) takes the skinny kernel: same epilogue semantics."""
+    A, B, acc = _operands(M, N, K, False, False, seed=21)
+    g = torch.Generator().manual_seed(22)
+    bias = torch.randn(N, generator=g).to(_dev())
+    r0 = torch.randn(M, N, generator=g).to(_dev())
+    r1 = torch.randn(M, N, generator=g).to(_dev())
+    out_f = torch.empty(M, N, device=_dev())
+    out_b = torch.empty(M, N, device=_dev(), dtype=torch.bfloat16)
+    L.gemm(A, B, M, N, K, bias=bias, res0=r0, res1=r1, out_f32=out_f, out_bf16=out_b, act=L.ACT_GELU)
+    torch.cuda.synchronize()
+    pre = acc + bias + r0 + r1
+    assert_close("skinny pre", out_f, pre, rtol=2e-5, atol=1e-4)
+    assert_close("skinny gelu", out_b, _gelu(pre), rtol=2 ** -8)
+
+
+@pytest.mark.parametrize("N,S,H,dk,dv,strict", [(3, 200, 2, 64, 64, False), (2, 64, 1, 64, 128, True), (4, 1024, 8, 64, 64, False)])
+def test_attention_decode_matches_full_attention(L, N, S, H, dk, dv, strict):
+    """Appending positions one at a time through the KV cache reproduces the rows of the full causal attention."""
+    q, k, v, do = _attn_inputs(N, S, H, dk, dv, seed=23)
+    o_ref, _, _, _, _ = _attn_ref(q, k, v, do, N, S, H, dk, dv, strict)
+    kc = torch.zeros(N * S, H * dk, device=_dev(), dtype=torch.bfloat16)
+    vc = torch.zeros(N * S, H * dv, device=_dev(), dtype=torch.bfloat16)
+    pos = torch.zeros(1, dtype=torch.int32, device=_dev())
+    qv, kv_, vv = q.view(N, S, -1), k.view(N, S, -1), v.view(N, S, -1)
+    o = torch.empty(N, H * dv, device=_dev(), dtype=torch.bfloat16)
+    steps = range(S) if S <= 256 else list(range(0, 40)) + list(range(S - 8, S))
+    if S > 256:  # pre-fill the caches for the skipped positions
+        kc.view(N, S, -1)[:] = kv_
+        vc.view(N, S, -1)[:] = vv
+    for p in steps:
+        pos.fill_(p)
+        L.attn_decode(qv[:, p].contiguous(), kv_[:, p].contiguous(), vv[:, p].contiguous(), kc, vc, o, pos, N, S, H, dk, dv, strict)
+        torch.cuda.synchronize()
+        assert_close(f"decode pos {p}", o, o_ref.view(N, S, -1)[:, p], rtol=2 ** -7, atol=2e-3)
+    assert torch.equal(kc.view(N, S, -1)[:, steps[-1]], kv_[:, steps[-1]])
+
+
 def test_gemm_strided_views(L):
     """q/k/v style column slices of a wider matrix as A, and a column slice as the output."""
     M, K, N = 512, 128, 192

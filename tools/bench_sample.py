@@ -17,3 +17,5 @@ t("eager, row-truncated      ")
 m._row_truncated_sampling = False
 t("eager, full forward       ")
 
+for k, v in m.__dict__.get("_samplers", {}).items():
+    print("sampler", k, "graph:", type(v["graph"]).__name__, v.get("graph_error", "")[:300])
