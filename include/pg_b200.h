@@ -73,7 +73,9 @@ typedef struct pg_gemm_epilogue {
 } pg_gemm_epilogue;
 
 /* impl: 0 = tcgen05/TMA kernel (the product); 1 = plain SIMT kernel kept as an on-device cross-check
- * for the tests (same epilogue code).  split_k >= 1 (only with accumulate=1 and no activation). */
+ * for the tests (same epilogue code); 2 = skinny-rows kernel for M <= 32 (the per-pixel step of incremental
+ * sampling: one warp per output column, weights streamed once).  split_k >= 1 (only with accumulate=1 and no
+ * activation). */
 int pg_gemm_bf16(const void* A, int a_mn_major, int64_t lda, const void* B, int b_mn_major, int64_t ldb,
                  int M, int N, int K, int split_k, const pg_gemm_epilogue* epi, int impl, void* stream);
 

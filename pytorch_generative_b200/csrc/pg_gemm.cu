@@ -765,9 +765,13 @@ extern "C" int pg_gemm_bf16(const void* A, int a_mn_major, int64_t lda, const vo
                                                                  reinterpret_cast<const bf16*>(B), b_mn_major, ldb, p);
     return pg_check_launch("pg_gemm_bf16(simt)");
   }
-  if (!a_mn_major && !b_mn_major && M <= 32 && !epi->accumulate && epi->dact == PG_ACT_NONE && K % 8 == 0 &&
-      (reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0 &&
-      (size_t)M * K * 2 <= 160 * 1024) {
+  if (impl == 2) {
+    // explicit opt-in (incremental sampling): never chosen implicitly, so forward() keeps one summation order
+    // whatever the number of rows
+    PG_REQUIRE(!a_mn_major && !b_mn_major && M <= 32 && !epi->accumulate && epi->dact == PG_ACT_NONE && K % 8 == 0 &&
+                   (reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0 &&
+                   (size_t)M * K * 2 <= 160 * 1024,
+               "pg_gemm_bf16(skinny): needs a K-major forward GEMM with M <= 32 rows (M=%d K=%d)", M, K);
     const size_t smem = (size_t)M * K * 2;
     PG_CUDA(cudaFuncSetAttribute(gemm_skinny_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     gemm_skinny_kernel<<<(N + 7) / 8, 256, smem, stream>>>(reinterpret_cast<const bf16*>(A), lda,

@@ -264,18 +264,19 @@ class ImageGPT(base.AutoregressiveModel):
         for b, blk in enumerate(self._transformer):
             wb = st["w"][b]
             a1, _, _, _ = ops.layernorm_fwd(xs, blk._ln1.weight.detach(), blk._ln1.bias.detach(), eps)
-            qkv, _, _ = ops.linear_fwd(a1, wb["wqkv"], wb["bqkv"])
+            qkv, _, _ = ops.linear_fwd(a1, wb["wqkv"], wb["bqkv"], skinny=True)
             q, k, v = qkv[:, : H * slot], qkv[:, H * slot: 2 * H * slot], qkv[:, 2 * H * slot:]
             o = torch.empty(n, H * wb["dv_slot"], dtype=BF16, device=xs.device)
             L.attn_decode(q, k, v, st["kc"][b], st["vc"][b], o, st["pos"], n, S, H, slot, wb["dv_slot"], False,
                           dk_true=wb["dk"])
-            _, _, hres = ops.linear_fwd(o, wb["wp"], blk._attn._proj.bias.detach(), res0=xs, want_bf16=False, want_f32=True)
+            _, _, hres = ops.linear_fwd(o, wb["wp"], blk._attn._proj.bias.detach(), res0=xs, want_bf16=False, want_f32=True,
+                                        skinny=True)
             a2, _, _, _ = ops.layernorm_fwd(hres, blk._ln2.weight.detach(), blk._ln2.bias.detach(), eps)
-            g, _, _ = ops.linear_fwd(a2, wb["w1"], blk._out[0].bias.detach(), act=L.ACT_GELU)
+            g, _, _ = ops.linear_fwd(a2, wb["w1"], blk._out[0].bias.detach(), act=L.ACT_GELU, skinny=True)
             _, _, xs = ops.linear_fwd(g, wb["w2"], blk._out[2].bias.detach(), res0=xs, res1=hres, want_bf16=False,
-                                      want_f32=True)
+                                      want_f32=True, skinny=True)
         af, _, _, _ = ops.layernorm_fwd(xs, self._ln.weight.detach(), self._ln.bias.detach(), eps)
-        _, _, logits = ops.linear_fwd(af, st["wo"], self._out.bias.detach(), want_bf16=False, want_f32=True)
+        _, _, logits = ops.linear_fwd(af, st["wo"], self._out.bias.detach(), want_bf16=False, want_f32=True, skinny=True)
         return logits
 
     def _sampler_state(self, n, c, h, w, device):
