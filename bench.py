@@ -216,11 +216,13 @@ def run_ours(args):
     if args.sample and rank == 0:
         # sample() latency (reference trainer.py:212-220 draws n=16): raster scan through the public API, wall clock
         model.eval()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        model.sample(n_samples=16)
-        torch.cuda.synchronize()
-        sample_ms = (time.perf_counter() - t0) * 1e3
+        sample_ms = []
+        for _ in range(2):  # first call builds the sampler (weight packing, graph capture), second is steady state
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            model.sample(n_samples=16)
+            torch.cuda.synchronize()
+            sample_ms.append((time.perf_counter() - t0) * 1e3)
 
     # ---- end-to-end: pinned host batch -> H2D -> step -> D2H scalars, through the Module API ----
     def e2e_step():
@@ -265,8 +267,11 @@ def run_ours(args):
         "last_loss": last[0], "last_grad_norm": last[1],
     }
     if sample_ms is not None:
-        out["sample"] = {"n_samples": 16, "pixels": spec["shape"][1] * spec["shape"][2], "ms": round(sample_ms, 1),
-                         "method": "reference semantics: one full forward per pixel (base.py:97-120)"}
+        out["sample"] = {"n_samples": 16, "pixels": spec["shape"][1] * spec["shape"][2],
+                         "ms_first_call": round(sample_ms[0], 1), "ms": round(sample_ms[1], 1),
+                         "method": "model.sample(n_samples=16): raster order and sample_fn hook of base.py:97-120; ImageGPT "
+                                   "evaluates each pixel incrementally (KV cache, graph-replayed step), the conv models "
+                                   "run one forward per pixel"}
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(spec, steps=2, warmup=1)
     print(json.dumps(out), flush=True)
