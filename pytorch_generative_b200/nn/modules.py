@@ -191,10 +191,12 @@ def image_positional_encoding(shape):
 # --------------------------------------------------------------------------------------------------
 # CausalAttention
 # --------------------------------------------------------------------------------------------------
-def head_slot_rows(n_heads, per_head, slot):
-    """Row indices that scatter `n_heads * per_head` projection rows into `slot`-wide head slots."""
+@functools.lru_cache(maxsize=64)
+def head_slot_rows(n_heads, per_head, slot, device=None, offset=0):
+    """Row indices that scatter `n_heads * per_head` projection rows into `slot`-wide head slots.  Cached per
+    device: the index tensor is built once, so steady-state calls issue no host->device copy (graph-capturable)."""
     idx = torch.arange(n_heads * per_head)
-    return (idx // per_head) * slot + idx % per_head
+    return ((idx // per_head) * slot + idx % per_head + offset).to(device)
 
 
 def pack_qkv_weights(q_w, q_b, kv_w, kv_b, n_heads, embed, out_ch, cin_q_pad, cin_kv_pad):
@@ -213,8 +215,8 @@ def pack_qkv_weights(q_w, q_b, kv_w, kv_b, n_heads, embed, out_ch, cin_q_pad, ci
         meta = dict(dk=dk, dv=dv, dv_slot=dv_slot, rows_q=None, rows_v=None, identity=True)
         return (ops.to_bf16(q_w.detach().reshape(embed, -1)), q_b.detach(),
                 ops.to_bf16(kv_w.detach().reshape(embed + out_ch, -1)), kv_b.detach(), meta)
-    rows_q = head_slot_rows(n_heads, dk, ops.HEAD_SLOT).to(dev)
-    rows_v = head_slot_rows(n_heads, dv, dv_slot).to(dev) + n_heads * ops.HEAD_SLOT
+    rows_q = head_slot_rows(n_heads, dk, ops.HEAD_SLOT, dev)
+    rows_v = head_slot_rows(n_heads, dv, dv_slot, dev, n_heads * ops.HEAD_SLOT)
     wq = torch.zeros(n_heads * ops.HEAD_SLOT, cin_q_pad, dtype=F32, device=dev)
     wq[rows_q, : q_w.shape[1]] = q_w.detach().reshape(q_w.shape[0], -1)
     bq = torch.zeros(n_heads * ops.HEAD_SLOT, dtype=F32, device=dev)
