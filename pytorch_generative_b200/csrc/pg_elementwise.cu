@@ -228,41 +228,61 @@ ln_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x, const f
   }
 }
 
+// Any channel count.  Warps walk rows with a grid stride; the column partial sums (dgamma, dbeta, column sums of
+// the emitted gradient) are accumulated per block in shared memory and flushed with one global atomic per column
+// and block.
 template <bool DY_BF16>
-__global__ void ln_bwd_generic_kernel(const void* __restrict__ dy_, const float* __restrict__ x,
-                                      const float* __restrict__ gamma, const float* __restrict__ mean_in,
-                                      const float* __restrict__ rstd_in, int P, int C, const float* __restrict__ dres0,
-                                      const float* __restrict__ dres1, float* __restrict__ dx_f32,
-                                      bf16* __restrict__ dx_bf16, float* __restrict__ dgamma,
-                                      float* __restrict__ dbeta, float* __restrict__ dx_colsum) {
+__global__ void __launch_bounds__(256)
+ln_bwd_generic_kernel(const void* __restrict__ dy_, const float* __restrict__ x, const float* __restrict__ gamma,
+                      const float* __restrict__ mean_in, const float* __restrict__ rstd_in, int P, int C,
+                      const float* __restrict__ dres0, const float* __restrict__ dres1, float* __restrict__ dx_f32,
+                      bf16* __restrict__ dx_bf16, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                      float* __restrict__ dx_colsum) {
+  extern __shared__ float ln_acc[];  // [3][C]
+  float* acc_g = ln_acc;
+  float* acc_b = ln_acc + C;
+  float* acc_s = ln_acc + 2 * C;
+  for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) ln_acc[i] = 0.f;
+  __syncthreads();
   const int lane = threadIdx.x & 31;
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= P) return;
-  const float mean = mean_in[row], rstd = rstd_in[row];
-  auto ld_dy = [&](int c) -> float {
-    return DY_BF16 ? __bfloat162float(reinterpret_cast<const bf16*>(dy_)[(size_t)row * C + c])
-                   : reinterpret_cast<const float*>(dy_)[(size_t)row * C + c];
-  };
-  float s1 = 0.f, s2 = 0.f;
-  for (int c = lane; c < C; c += 32) {
-    const float xh = (x[(size_t)row * C + c] - mean) * rstd;
-    const float d = ld_dy(c);
-    const float gy = d * gamma[c];
-    s1 += gy;
-    s2 += gy * xh;
-    if (dgamma) atomicAdd(dgamma + c, d * xh);
-    if (dbeta) atomicAdd(dbeta + c, d);
+  const int warps_per_block = blockDim.x >> 5;
+  const int num_warps = gridDim.x * warps_per_block;
+  const bool want_cols = dgamma || dbeta;
+  for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < P; row += num_warps) {
+    const float mean = mean_in[row], rstd = rstd_in[row];
+    const size_t base = (size_t)row * C;
+    auto ld_dy = [&](int c) -> float {
+      return DY_BF16 ? __bfloat162float(reinterpret_cast<const bf16*>(dy_)[base + c])
+                     : reinterpret_cast<const float*>(dy_)[base + c];
+    };
+    float s1 = 0.f, s2 = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      const float xh = (x[base + c] - mean) * rstd;
+      const float d = ld_dy(c);
+      const float gy = d * gamma[c];
+      s1 += gy;
+      s2 += gy * xh;
+      if (want_cols) {
+        atomicAdd(acc_g + c, d * xh);
+        atomicAdd(acc_b + c, d);
+      }
+    }
+    const float m1 = warp_sum(s1) / C, m2 = warp_sum(s2) / C;
+    for (int c = lane; c < C; c += 32) {
+      const float xh = (x[base + c] - mean) * rstd;
+      float o = rstd * (ld_dy(c) * gamma[c] - m1 - xh * m2);
+      if (dres0) o += dres0[base + c];
+      if (dres1) o += dres1[base + c];
+      if (dx_colsum) atomicAdd(acc_s + c, o);
+      if (dx_f32) dx_f32[base + c] = o;
+      if (dx_bf16) dx_bf16[base + c] = __float2bfloat16(o);
+    }
   }
-  const float m1 = warp_sum(s1) / C, m2 = warp_sum(s2) / C;
-  for (int c = lane; c < C; c += 32) {
-    const float xh = (x[(size_t)row * C + c] - mean) * rstd;
-    float o = rstd * (ld_dy(c) * gamma[c] - m1 - xh * m2);
-    const size_t off = (size_t)row * C + c;
-    if (dres0) o += dres0[off];
-    if (dres1) o += dres1[off];
-    if (dx_colsum) atomicAdd(dx_colsum + c, o);
-    if (dx_f32) dx_f32[off] = o;
-    if (dx_bf16) dx_bf16[off] = __float2bfloat16(o);
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    if (dgamma) atomicAdd(dgamma + c, acc_g[c]);
+    if (dbeta) atomicAdd(dbeta + c, acc_b[c]);
+    if (dx_colsum) atomicAdd(dx_colsum + c, acc_s[c]);
   }
 }
 
@@ -515,12 +535,14 @@ extern "C" int pg_layernorm_bwd(const void* dy_bf16, const float* dy_f32, const 
 #undef LNB_CASE
     }
   } else {
-    const int blocks = (P + wpb - 1) / wpb;
+    PG_REQUIRE(C <= 4096, "pg_layernorm_bwd: more than 4096 channels");
+    const int blocks = grid_for((long long)P * 32, threads, 4);
+    const size_t smem = 3 * (size_t)C * sizeof(float);
     if (dy_bf16)
-      ln_bwd_generic_kernel<true><<<blocks, threads, 0, stream>>>(dy_bf16, x, gamma, mean, rstd, P, C, dres0, dres1,
+      ln_bwd_generic_kernel<true><<<blocks, threads, smem, stream>>>(dy_bf16, x, gamma, mean, rstd, P, C, dres0, dres1,
                                                                   dx_f32, dxb, dgamma, dbeta, dx_colsum);
     else
-      ln_bwd_generic_kernel<false><<<blocks, threads, 0, stream>>>(dy_f32, x, gamma, mean, rstd, P, C, dres0, dres1,
+      ln_bwd_generic_kernel<false><<<blocks, threads, smem, stream>>>(dy_f32, x, gamma, mean, rstd, P, C, dres0, dres1,
                                                                    dx_f32, dxb, dgamma, dbeta, dx_colsum);
   }
   return pg_check_launch("pg_layernorm_bwd");
