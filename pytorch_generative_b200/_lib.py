@@ -14,7 +14,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpg_b200.so")
+# PG_B200_LIB: developer knob to load an alternative build of the same ABI (kernel A/B experiments)
+LIB_PATH = os.environ.get("PG_B200_LIB") or os.path.join(_HERE, "libpg_b200.so")
 
 ACT_NONE, ACT_RELU, ACT_GELU, ACT_ELU, ACT_TANH = 0, 1, 2, 3, 4
 ACT_BY_NAME = {None: ACT_NONE, "none": ACT_NONE, "relu": ACT_RELU, "gelu": ACT_GELU, "elu": ACT_ELU, "tanh": ACT_TANH}

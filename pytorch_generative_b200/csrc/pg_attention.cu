@@ -7,6 +7,8 @@
 //
 // impl 1 (this section): SIMT kernels, one warp per row — the on-device cross-check used by the tests.
 // impl 0: tensor-core kernels (pg_attention_tc.cuh), the product path.
+#include <type_traits>
+
 #include "../../include/pg_b200.h"
 #include "pg_common.cuh"
 

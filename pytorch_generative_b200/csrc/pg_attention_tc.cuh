@@ -8,9 +8,12 @@
 //
 // Forward, one CTA per (image, head, 128-query tile), 2 CTAs co-resident per SM (DV = 64):
 //   warp 4   TMA producer (Q once, K/V ring of 2)
-//   warp 5   TMEM allocator + MMA issuer:  S = Q K^T (TMEM cols [0,128)),  PV = P V (cols [128,128+DV))
+//   warp 5   TMEM allocator + MMA issuer:  S = Q K^T (TMEM cols [0,128)),  PV = P V (two buffers of DV columns).
+//            Once P(j) is in smem it issues S(j+1) *before* P(j) V(j), so the next score tile is ready while the
+//            softmax threads fold the previous PV into their running output.
 //   warps 0-3 one query row per thread: two passes over S in TMEM (max, then exp2 + sum), P (bf16) to smem,
-//            running output kept in registers: O = O * alpha + PV.
+//            running output kept in registers: O = (O + PV(j-1)) * alpha_j.  Only the diagonal tile runs the
+//            masked code path.
 // Backward, one CTA per (image, head, 128-key tile), looping over query tiles i >= j:
 //   S = Q_i K_j^T, dP = dO_i V_j^T -> P = exp2(S*c - lse), dS = P * (dP - delta) (bf16 to smem) ->
 //   dV_j += P^T dO_i, dK_j += dS^T Q_i (accumulated in TMEM), dQ_i = dS K_j (fp32 atomics into dq_accum).
@@ -71,7 +74,7 @@ template <int DV>
 __global__ void __launch_bounds__(192, DV == 64 ? 2 : 1)
 attn_fwd_tc_kernel(const __grid_constant__ AttnTmaps tm, const AttnArgs a, const int T) {
   constexpr int V_BYTES = DV * 256;
-  constexpr int TMEM_COLS = 256;
+  constexpr int TMEM_COLS = (DV == 64) ? 256 : 512;  // S (128) + two PV buffers (2 x DV)
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + ATOM_BYTES;          // 2 stages
@@ -137,14 +140,8 @@ attn_fwd_tc_kernel(const __grid_constant__ AttnTmaps tm, const AttnArgs a, const
       umma_commit(s_full);
       for (int j = 0; j < ntiles; ++j) {
         const int st = j & 1;
-        mbar_wait(p_full, j & 1);
+        mbar_wait(p_full, j & 1);  // P(j) in smem; every softmax thread is done reading S(j)
         tc_fence_after();
-        const uint32_t v_addr = smem_u32(sV + st * V_BYTES);
-#pragma unroll
-        for (int kk = 0; kk < 8; ++kk)
-          umma_bf16_ss(tmem_o, desc_kmajor(p_addr, kk), desc_mnmajor(v_addr, kk), idesc_o, kk > 0);
-        umma_commit(o_full);
-        umma_commit(&kv_empty[st]);
         if (j + 1 < ntiles) {
           const int sn = (j + 1) & 1;
           mbar_wait(&kv_full[sn], ((j + 1) >> 1) & 1);
@@ -155,6 +152,12 @@ attn_fwd_tc_kernel(const __grid_constant__ AttnTmaps tm, const AttnArgs a, const
             umma_bf16_ss(tmem_s, desc_kmajor(q_addr, kk), desc_kmajor(k_addr, kk), idesc_s, kk > 0);
           umma_commit(s_full);
         }
+        const uint32_t v_addr = smem_u32(sV + st * V_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)
+          umma_bf16_ss(tmem_o + st * DV, desc_kmajor(p_addr, kk), desc_mnmajor(v_addr, kk), idesc_o, kk > 0);
+        umma_commit(o_full);
+        umma_commit(&kv_empty[st]);
       }
     }
   } else {
@@ -168,66 +171,81 @@ attn_fwd_tc_kernel(const __grid_constant__ AttnTmaps tm, const AttnArgs a, const
     float O[DV];
 #pragma unroll
     for (int d = 0; d < DV; ++d) O[d] = 0.f;
-    for (int j = 0; j < ntiles; ++j) {
-      mbar_wait(s_full, j & 1);
-      tc_fence_after();
-      const bool diag = (j == i);
-      const int k0 = j * AT;
-      float mx = m;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(tmem_s + lane_base + c * 32, v);
-        tmem_wait_ld();
-#pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          float s = __uint_as_float(v[e]);
-          if (diag && (k0 + c * 32 + e > qlim)) s = -INFINITY;
-          mx = fmaxf(mx, s);
-        }
-      }
-      const float m_use = (mx == -INFINITY) ? 0.f : mx;
-      const float alpha = fast_exp2((m - m_use) * sl2);  // m = -inf -> 0
-      const float mb = m_use * sl2;
-      float lt = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(tmem_s + lane_base + c * 32, v);
-        tmem_wait_ld();
-        uint32_t w[16];
-#pragma unroll
-        for (int e = 0; e < 32; e += 2) {
-          float p0 = fast_exp2(fmaf(__uint_as_float(v[e]), sl2, -mb));
-          float p1 = fast_exp2(fmaf(__uint_as_float(v[e + 1]), sl2, -mb));
-          if (diag) {
-            if (k0 + c * 32 + e > qlim) p0 = 0.f;
-            if (k0 + c * 32 + e + 1 > qlim) p1 = 0.f;
-          }
-          lt += p0 + p1;
-          w[e >> 1] = pack_bf16x2(p0, p1);
-        }
-        store_tile_row_chunk(sP, r, c, w);
-      }
-      fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
-      tc_fence_before();
-      mbar_arrive(p_full);
-      l = l * alpha + lt;
-      m = mx;
-#pragma unroll
-      for (int d = 0; d < DV; ++d) O[d] *= alpha;
-      mbar_wait(o_full, j & 1);
-      tc_fence_after();
+    // O += PV(jj): the tensor core wrote it to output buffer jj & 1
+    auto fold_pv = [&](int jj) {
 #pragma unroll
       for (int c = 0; c < DV / 32; ++c) {
         uint32_t v[32];
-        tmem_ld_32x32b_x32(tmem_o + lane_base + c * 32, v);
+        tmem_ld_32x32b_x32(tmem_o + (jj & 1) * DV + lane_base + c * 32, v);
         tmem_wait_ld();
 #pragma unroll
         for (int e = 0; e < 32; ++e) O[c * 32 + e] += __uint_as_float(v[e]);
       }
+    };
+    for (int j = 0; j < ntiles; ++j) {
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      const int k0 = j * AT;
+      float mx = m, lt = 0.f, alpha = 1.f;
+      // One score tile: running max, then P = exp2(s * c - m * c) to smem.  MASK is a compile-time flag so that only
+      // the diagonal tile pays for the per-element causal compare / select.
+      auto softmax_tile = [&](auto masked) {
+        constexpr bool MASK = decltype(masked)::value;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tmem_s + lane_base + c * 32, v);
+          tmem_wait_ld();
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            float sc = __uint_as_float(v[e]);
+            if (MASK && (k0 + c * 32 + e > qlim)) sc = -INFINITY;
+            mx = fmaxf(mx, sc);
+          }
+        }
+        const float m_use = (mx == -INFINITY) ? 0.f : mx;
+        alpha = fast_exp2((m - m_use) * sl2);  // m = -inf -> 0
+        const float mb = m_use * sl2;
+        if (j > 0) {  // P(j-1) V(j-1) complete: sP may be overwritten, and its result is ready to be folded in
+          mbar_wait(o_full, (j - 1) & 1);
+          tc_fence_after();
+        }
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tmem_s + lane_base + c * 32, v);
+          tmem_wait_ld();
+          uint32_t w[16];
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) {
+            float p0 = fast_exp2(fmaf(__uint_as_float(v[e]), sl2, -mb));
+            float p1 = fast_exp2(fmaf(__uint_as_float(v[e + 1]), sl2, -mb));
+            if (MASK) {
+              if (k0 + c * 32 + e > qlim) p0 = 0.f;
+              if (k0 + c * 32 + e + 1 > qlim) p1 = 0.f;
+            }
+            lt += p0 + p1;
+            w[e >> 1] = pack_bf16x2(p0, p1);
+          }
+          store_tile_row_chunk(sP, r, c, w);
+        }
+      };
+      if (j == i) softmax_tile(std::true_type{});
+      else softmax_tile(std::false_type{});
+      fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
       tc_fence_before();
+      mbar_arrive(p_full);
+      // off the critical path (the tensor core is computing S(j+1) now): O = (O + PV(j-1)) * alpha_j
+      if (j > 0) fold_pv(j - 1);
+      l = l * alpha + lt;
+      m = mx;
+#pragma unroll
+      for (int d = 0; d < DV; ++d) O[d] *= alpha;
     }
+    mbar_wait(o_full, (ntiles - 1) & 1);
+    tc_fence_after();
+    fold_pv(ntiles - 1);
+    tc_fence_before();
     if (qi < a.S) {
       const float inv = l > 0.f ? 1.f / l : 0.f;
       bf16* orow = a.out + ((size_t)n * a.S + qi) * a.ld_o + h * DV;
@@ -254,11 +272,14 @@ attn_fwd_tc_kernel(const __grid_constant__ AttnTmaps tm, const AttnArgs a, const
 // Thread layout (320 threads): warps 0-3 = softmax group A (key columns 0-63 of the tile), warps 4-7 = group B
 // (columns 64-127); thread = query row (TMEM lane) in both groups.  Warp 8 = TMA producer, warp 9 = TMEM owner + MMA
 // issuer.  Per query tile there are exactly two hand-offs:
-//   MMA phase    : dV += P^T dO, dK += dS^T Q, dQ = dS K  (tile i)   then   S = Q K^T, dP = dO V^T  (tile i+1)
-//   thread phase : read out dQ(i) (-> fp32 staging -> TMA reduce-add), then softmax / dS of tile i+1
-// so the tensor core runs five MMAs back to back and the exp/convert work of the 256 softmax threads is the only
-// other serial stage.
+//   MMA phase    : dQ = dS K (tile i), S = Q K^T, dP = dO V^T (tile i+1)  -> s_full,
+//                  then dV += P^T dO, dK += dS^T Q (tile i)                -> pds_empty (P / dS tiles reusable)
+//   thread phase : read out dQ(i) (-> fp32 staging -> TMA reduce-add), softmax / dS of tile i+1 (stored once
+//                  pds_empty says the tensor core no longer reads tile i's P / dS)
+// so the two accumulating products that nobody waits for run underneath the exp/convert work of the 256 softmax
+// threads, and only three of the five products sit on the serial chain.
 template <int DV>
+// (168 registers is the ceiling for 10 warps: three of them share one 16K-register scheduler partition)
 __global__ void __launch_bounds__(320, 1)
 attn_bwd_tc_kernel(const __grid_constant__ AttnTmaps tm, const AttnArgs a, const int T) {
   constexpr int V_BYTES = DV * 256;
@@ -279,6 +300,7 @@ attn_bwd_tc_kernel(const __grid_constant__ AttnTmaps tm, const AttnArgs a, const
   uint64_t* qdo_empty = bars + 3;  // [2]
   uint64_t* s_full = bars + 5;     // S/dP of the next tile (and dQ of the previous one) complete
   uint64_t* pds_full = bars + 6;   // P and dS written to smem (256 arrivals)
+  uint64_t* pds_empty = bars + 7;  // dV / dK products of the tile have finished reading P and dS
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -293,6 +315,7 @@ attn_bwd_tc_kernel(const __grid_constant__ AttnTmaps tm, const AttnArgs a, const
     for (int s = 0; s < 2; ++s) { mbar_init(&qdo_full[s], 1); mbar_init(&qdo_empty[s], 1); }
     mbar_init(s_full, 1);
     mbar_init(pds_full, 256);
+    mbar_init(pds_empty, 1);
     fence_barrier_init();
     fence_proxy_async_smem();
   }
@@ -345,21 +368,23 @@ attn_bwd_tc_kernel(const __grid_constant__ AttnTmaps tm, const AttnArgs a, const
         mbar_wait(pds_full, it & 1);
         tc_fence_after();
 #pragma unroll
+        for (int kk = 0; kk < 8; ++kk)  // K = 128 keys
+          umma_bf16_ss(tmem + COL_DQ, desc_kmajor(ds_addr, kk), desc_mnmajor(k_addr, kk), idesc_dq, kk > 0);
+        if (it + 1 < niter) {
+          mbar_wait(&qdo_full[st ^ 1], ((it + 1) >> 1) & 1);
+          tc_fence_after();
+          issue_s_dp(st ^ 1);
+          umma_commit(s_full);  // dQ(it) and S/dP(it+1) complete
+        }
+#pragma unroll
         for (int kk = 0; kk < 8; ++kk)  // K = 128 queries
           umma_bf16_ss(tmem + COL_DV, desc_mnmajor(p_addr, kk), desc_mnmajor(do_addr, kk), idesc_dv, (it > 0 || kk > 0));
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)
           umma_bf16_ss(tmem + COL_DK, desc_mnmajor(ds_addr, kk), desc_mnmajor(q_addr, kk), idesc_dk, (it > 0 || kk > 0));
-#pragma unroll
-        for (int kk = 0; kk < 8; ++kk)  // K = 128 keys
-          umma_bf16_ss(tmem + COL_DQ, desc_kmajor(ds_addr, kk), desc_mnmajor(k_addr, kk), idesc_dq, kk > 0);
         umma_commit(&qdo_empty[st]);  // Q_i / dO_i stage reusable once these complete
-        if (it + 1 < niter) {
-          mbar_wait(&qdo_full[st ^ 1], ((it + 1) >> 1) & 1);
-          tc_fence_after();
-          issue_s_dp(st ^ 1);
-        }
-        umma_commit(s_full);  // dQ(it) [+ S/dP(it+1)] complete
+        umma_commit(pds_empty);       // ... and so are the P / dS tiles
+        if (it + 1 == niter) umma_commit(s_full);  // last tile: dQ and the whole dV / dK accumulation complete
       }
     }
   } else {
@@ -413,6 +438,9 @@ attn_bwd_tc_kernel(const __grid_constant__ AttnTmaps tm, const AttnArgs a, const
       const bool need_mask = (it == 0) || (i == T - 1);
       mbar_wait(s_full, it & 1);
       tc_fence_after();
+      // the tensor core may still be reading tile i-1's P / dS (dV, dK run after S/dP): wait before the first write
+      // into those tiles -- which is the dQ staging itself when it aliases sP
+      if (!DQ_OWN_STAGING && it > 0) mbar_wait(pds_empty, (it - 1) & 1);
       if (it > 0) flush_dq(i - 1);
       // all four TMEM loads of this thread's 64 columns are issued before the single wait (ILP: the exp / convert
       // chains of the two chunks then interleave), results go to the swizzled P / dS tiles
@@ -423,26 +451,33 @@ attn_bwd_tc_kernel(const __grid_constant__ AttnTmaps tm, const AttnArgs a, const
         tmem_ld_32x32b_x32(tmem + COL_DP + lane_base + (grp * 2 + cc) * 32, dv[cc]);
       }
       tmem_wait_ld();
+      if (DQ_OWN_STAGING && it > 0) mbar_wait(pds_empty, (it - 1) & 1);
+      // MASK is a compile-time flag: only the diagonal tile and the ragged last tile pay for the compare / select
+      auto p_ds_tile = [&](auto masked) {
+        constexpr bool MASK = decltype(masked)::value;
 #pragma unroll
-      for (int cc = 0; cc < 2; ++cc) {
-        const int c = grp * 2 + cc;
-        uint32_t pw[16], dw[16];
+        for (int cc = 0; cc < 2; ++cc) {
+          const int c = grp * 2 + cc;
+          uint32_t pw[16], dw[16];
 #pragma unroll
-        for (int e = 0; e < 32; e += 2) {
-          float p0 = fast_exp2(fmaf(__uint_as_float(sv[cc][e]), sl2, -lse2));
-          float p1 = fast_exp2(fmaf(__uint_as_float(sv[cc][e + 1]), sl2, -lse2));
-          if (need_mask) {
-            if (k0 + c * 32 + e > qlim) p0 = 0.f;
-            if (k0 + c * 32 + e + 1 > qlim) p1 = 0.f;
+          for (int e = 0; e < 32; e += 2) {
+            float p0 = fast_exp2(fmaf(__uint_as_float(sv[cc][e]), sl2, -lse2));
+            float p1 = fast_exp2(fmaf(__uint_as_float(sv[cc][e + 1]), sl2, -lse2));
+            if (MASK) {
+              if (k0 + c * 32 + e > qlim) p0 = 0.f;
+              if (k0 + c * 32 + e + 1 > qlim) p1 = 0.f;
+            }
+            const float d0 = p0 * (__uint_as_float(dv[cc][e]) - delta);
+            const float d1 = p1 * (__uint_as_float(dv[cc][e + 1]) - delta);
+            pw[e >> 1] = pack_bf16x2(p0, p1);
+            dw[e >> 1] = pack_bf16x2(d0, d1);
           }
-          const float d0 = p0 * (__uint_as_float(dv[cc][e]) - delta);
-          const float d1 = p1 * (__uint_as_float(dv[cc][e + 1]) - delta);
-          pw[e >> 1] = pack_bf16x2(p0, p1);
-          dw[e >> 1] = pack_bf16x2(d0, d1);
+          store_tile_row_chunk(sP, r, c, pw);
+          store_tile_row_chunk(sdS, r, c, dw);
         }
-        store_tile_row_chunk(sP, r, c, pw);
-        store_tile_row_chunk(sdS, r, c, dw);
-      }
+      };
+      if (need_mask) p_ds_tile(std::true_type{});
+      else p_ds_tile(std::false_type{});
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(pds_full);

@@ -93,11 +93,31 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 #ifndef PG_MBAR_TIMEOUT_CYCLES
 #define PG_MBAR_TIMEOUT_CYCLES (4000000000ll)
 #endif
+#ifndef PG_MBAR_SUSPEND_NS
+#define PG_MBAR_SUSPEND_NS 20000
+#endif
+// try_wait with an explicit suspend-time hint: the waiting thread is parked by the hardware (it issues nothing) until
+// the phase completes or `ns` nanoseconds pass, instead of re-polling through the issue slots of its scheduler.
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > PG_MBAR_TIMEOUT_CYCLES) {
+  long long t0 = 0;
+  uint32_t spins = 0;
+  while (!(PG_MBAR_SUSPEND_NS ? mbar_try_wait_hint(bar, parity, PG_MBAR_SUSPEND_NS) : mbar_try_wait(bar, parity))) {
+    if ((++spins & 255u) != 0) continue;  // the clock is only read every 256 wake-ups
+    if (t0 == 0) {
+      t0 = clock64();
+    } else if (clock64() - t0 > PG_MBAR_TIMEOUT_CYCLES) {
       printf("pg: mbarrier wait timed out (block %d thread %d bar smem 0x%x parity %u)\n", blockIdx.x,
              threadIdx.x, smem_u32(bar), parity);
       __trap();

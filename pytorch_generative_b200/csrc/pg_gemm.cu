@@ -198,8 +198,12 @@ __device__ __forceinline__ void slab_bf16_store(uint8_t* slab, int r, const floa
 // its half (BN/2 rows) of B, the leader issues M = 256 MMAs that read both CTAs' shared memory, each CTA owns the
 // accumulator rows of its half in its own TMEM and runs its own epilogue.  Halves the L2 -> SM operand traffic per flop
 // (64 instead of 96 B/cycle/SM at BN = 256), which is what bounds the 1-CTA kernel.
-template <int BN, bool A_MN, bool B_MN, bool TWO>
-__global__ void __launch_bounds__(384, 1)
+// Epilogue warpgroups per CTA (each 4 warps = the four TMEM lane quarters).  More groups = more warps to hide the
+// TMEM-load / shared-memory / barrier latencies of the epilogue; the register budget per thread shrinks accordingly.
+// Two groups (384 threads, 168 registers) is the default; the short-K pair kernels, whose tile time is mostly
+// epilogue, are also built with three (512 threads, 126 registers) -- see dispatch_bn.
+template <int BN, bool A_MN, bool B_MN, bool TWO, int EPI_GROUPS>
+__global__ void __launch_bounds__(128 + 128 * EPI_GROUPS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ EpiMaps em, const GemmParams p) {
   static_assert(!TWO || (!A_MN && BN == 256), "the 2-CTA kernel is the K-major-A, 256-wide variant");
@@ -219,12 +223,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int STAGES = p.stages;
   uint8_t* epi_smem = smem + STAGES * STAGE_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_smem + 2 * p.epi_depth * p.epi_stage_bytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_smem + EPI_GROUPS * p.epi_depth * p.epi_stage_bytes);
   uint64_t* empty_bar = full_bar + MAX_STAGES;
   uint64_t* tfull_bar = empty_bar + MAX_STAGES;
   uint64_t* tempty_bar = tfull_bar + ACC_STAGES;
-  uint64_t* in_full = tempty_bar + ACC_STAGES;  // [2 groups][2 stages] epilogue input slabs landed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(in_full + 4);
+  uint64_t* in_full = tempty_bar + ACC_STAGES;  // [groups][2 stages] epilogue input slabs landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(in_full + 2 * EPI_GROUPS);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -243,9 +247,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int i = 0; i < ACC_STAGES; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], TWO ? 16 : 8);  // one arrive per epilogue warp (2 groups x 4), of both CTAs if paired
+      mbar_init(&tempty_bar[i], (TWO ? 8 : 4) * EPI_GROUPS);  // one arrive per epilogue warp, of both CTAs if paired
     }
-    for (int i = 0; i < 4; ++i) mbar_init(&in_full[i], 1);
+    for (int i = 0; i < 2 * EPI_GROUPS; ++i) mbar_init(&in_full[i], 1);
     fence_barrier_init();
     fence_proxy_async_smem();
   }
@@ -355,9 +359,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue: two warpgroups, alternating 32-column chunks =====================
+    // ===================== epilogue: EPI_GROUPS warpgroups, round-robin over 32-column chunks =====================
     // Warp w may only touch TMEM lanes [32*(w%4), +32), so warps 4..7 (group 0) and 8..11 (group 1) cover the
-    // same 128 rows; group g owns every chunk whose position in this CTA's chunk sequence has parity g, its own
+    // same 128 rows; group g owns every chunk whose position in this CTA's chunk sequence is g mod EPI_GROUPS, its own
     // staging stage, input barrier and named barrier.  Two groups double the issue slots of the epilogue math.
     const int grp = (warp - 4) >> 2;
     const int ew = warp & 3;        // TMEM lane quarter
@@ -391,7 +395,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     };
     if (p.staged && p.in_bytes > 0 && leader) {
       prefetch_pos(grp, 0);
-      if (depth > 1) prefetch_pos(grp + 2, 1);
+      if (depth > 1) prefetch_pos(grp + EPI_GROUPS, 1);
     }
     __syncwarp();
 
@@ -405,7 +409,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int row = m_blk * MT + (int)rank * BM + r;
 #pragma unroll 1
       for (int c = 0; c < NCH; ++c, ++gc) {
-        if ((gc & 1u) != (unsigned)grp) continue;  // the other group's chunk
+        if ((gc % (unsigned)EPI_GROUPS) != (unsigned)grp) continue;  // another group's chunk
         const int col0 = n_blk * BN + c * 32;
         uint32_t acc[32];
         tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * BN + c * 32, acc);
@@ -479,7 +483,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (p.off_outp >= 0) tma_store_2d(&em.out_pre, base + p.off_outp, col0, row0);
           if (p.off_outb >= 0) tma_store_2d(&em.out_bf16, base + p.off_outb, col0, row0);
           tma_store_commit();
-          if (p.in_bytes > 0) prefetch_pos(gc + 2 * depth, st);  // refill this stage for this group's chunk `depth` ahead
+          if (p.in_bytes > 0) prefetch_pos(gc + EPI_GROUPS * depth, st);  // refill this stage for this group's chunk `depth` ahead
         }
         ++used;
         __syncwarp();
@@ -597,7 +601,7 @@ gemm_skinny_kernel(const bf16* __restrict__ A, int64_t lda, const bf16* __restri
   }
 }
 
-template <int BN, bool A_MN, bool B_MN, bool TWO = false>
+template <int BN, bool A_MN, bool B_MN, bool TWO = false, int EPI_GROUPS = 2>
 int launch_tc(const void* A, int64_t lda, const void* B, int64_t ldb, GemmParams& p, cudaStream_t stream) {
   constexpr int B_ROWS = TWO ? BN / 2 : BN;
   if (TWO) p.num_m_blk = (p.M + 2 * BM - 1) / (2 * BM);
@@ -643,20 +647,21 @@ int launch_tc(const void* A, int64_t lda, const void* B, int64_t ldb, GemmParams
   // two staging stages per epilogue group when that still leaves a >= 3-deep operand pipeline
   // (short-K tiles only: there the epilogue is a large share of the tile time; long-K tiles want the smem for
   // a deeper operand pipeline instead)
-  p.epi_depth = (p.staged && p.k_per_split <= 16 && (SMEM_LIMIT - 4 * p.epi_stage_bytes - 1536) / STAGE_BYTES >= 3) ? 2 : 1;
-  const int fixed = 2 * p.epi_depth * p.epi_stage_bytes + 1024 /*align slack*/ + 512 /*barriers*/;
+  p.epi_depth = (p.staged && p.k_per_split <= 16 && (SMEM_LIMIT - 2 * EPI_GROUPS * p.epi_stage_bytes - 1536) / STAGE_BYTES >= 3) ? 2 : 1;
+  const int fixed = EPI_GROUPS * p.epi_depth * p.epi_stage_bytes + 1024 /*align slack*/ + 512 /*barriers*/;
   int stages = (SMEM_LIMIT - fixed) / STAGE_BYTES;
   if (stages > 8) stages = 8;
   if (stages > p.k_iters + 1) stages = p.k_iters + 1 > 2 ? p.k_iters + 1 : 2;
   PG_REQUIRE(stages >= 2, "pg_gemm_bf16: epilogue staging leaves no room for the operand pipeline (BN=%d)", BN);
   p.stages = stages;
   const int smem_bytes = stages * STAGE_BYTES + fixed;
-  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, TWO>;
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, TWO, EPI_GROUPS>;
+  constexpr int GEMM_THREADS = 128 + 128 * EPI_GROUPS;
   PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
   const int num_tiles = p.num_m_blk * p.num_n_blk * p.splits;
   if (!TWO) {
     const int grid = min(num_tiles, pg_num_sms());
-    kern<<<grid, 384, smem_bytes, stream>>>(tmA, tmB, em, p);
+    kern<<<grid, GEMM_THREADS, smem_bytes, stream>>>(tmA, tmB, em, p);
     return pg_check_launch("pg_gemm_bf16(tcgen05)");
   }
   // CTA pairs: clusters of 2 along x, one pair per tile stream
@@ -664,7 +669,7 @@ int launch_tc(const void* A, int64_t lda, const void* B, int64_t ldb, GemmParams
   if (pairs > num_tiles) pairs = num_tiles;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * pairs);
-  cfg.blockDim = dim3(384);
+  cfg.blockDim = dim3(GEMM_THREADS);
   cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -697,9 +702,15 @@ int dispatch_bn(const void* A, int64_t lda, const void* B, int64_t ldb, GemmPara
     // 74 pairs, and room for >= 3 operand stages of 32 KB next to the epilogue slabs.
     static const bool no_pairs = getenv("PG_GEMM_NO_PAIRS") != nullptr;
     const int tiles = ((p.M + 255) / 256) * ((p.N + 255) / 256);
-    const bool fits = !staged || (SMEM_LIMIT - 2 * epi - 1536) / (A_STAGE_BYTES + 128 * BK * 2) >= 3;
+    constexpr int PAIR_STAGE = A_STAGE_BYTES + 128 * BK * 2;
+    const bool fits = !staged || (SMEM_LIMIT - 2 * epi - 1536) / PAIR_STAGE >= 3;
     if (!no_pairs && bn == 256 && p.splits == 1 && tiles >= pg_num_sms() / 2 && fits) {
       p.num_n_blk = (p.N + 255) / 256;
+      // Short-K tiles (K <= 1024) spend most of their time in the epilogue: a third epilogue warpgroup hides more
+      // of its latency, provided its two extra staging stages still leave a 3-deep operand pipeline.
+      static const bool no_g3 = getenv("PG_GEMM_NO_G3") != nullptr;
+      if (!no_g3 && staged && p.k_iters <= 16 && (SMEM_LIMIT - 6 * epi - 1536) / PAIR_STAGE >= 3)
+        return launch_tc<256, false, B_MN, true, 3>(A, lda, B, ldb, p, stream);
       return launch_tc<256, false, B_MN, true>(A, lda, B, ldb, p, stream);
     }
   }
