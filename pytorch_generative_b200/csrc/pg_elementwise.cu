@@ -3,6 +3,8 @@
 // Module boundary.  All are pure streaming kernels: 16-byte vector accesses, one pass over the data,
 // fp32 math, row statistics by warp shuffles.
 #include "../../include/pg_b200.h"
+#include <stdlib.h>
+
 #include "pg_common.cuh"
 
 namespace {
@@ -134,7 +136,7 @@ ln_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x, const f
               bf16* __restrict__ dx_bf16, float* __restrict__ dgamma, float* __restrict__ dbeta,
               float* __restrict__ dx_colsum) {
   constexpr int C = 128 * V;
-  __shared__ float red[8][33];
+  __shared__ float red[3 * C];
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
   const int warps_per_block = blockDim.x >> 5;
@@ -202,28 +204,32 @@ ln_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x, const f
     }
   }
   // Block reduction of the per-lane column partials (dgamma, dbeta, column sums of the emitted gradient = the
-  // bias gradient of the layer that produced x): transpose through shared memory, one atomic per column.
+  // bias gradient of the layer that produced x): every warp adds its partials into one shared [3][C] array
+  // (shared-memory atomics, one pass), then one global atomic per column and block.
   if (dgamma || dbeta || dx_colsum) {
+    for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) red[i] = 0.f;
+    __syncthreads();
 #pragma unroll
     for (int i = 0; i < V; ++i) {
-#pragma unroll
-      for (int which = 0; which < 3; ++which) {
-        const float4 val = which == 0 ? dg[i] : (which == 1 ? db[i] : ds[i]);
-        float* dst = which == 0 ? dgamma : (which == 1 ? dbeta : dx_colsum);
-        if (dst == nullptr) continue;  // uniform across the block
-        const float comp[4] = {val.x, val.y, val.z, val.w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          __syncthreads();
-          red[wib][lane] = comp[j];
-          __syncthreads();
-          if (wib == 0) {
-            float t = 0.f;
-            for (int w = 0; w < warps_per_block; ++w) t += red[w][lane];
-            if (dst) atomicAdd(dst + (i * 32 + lane) * 4 + j, t);
-          }
-        }
+      const int c0 = (i * 32 + lane) * 4;
+      if (dgamma) {
+        atomicAdd(&red[c0], dg[i].x); atomicAdd(&red[c0 + 1], dg[i].y);
+        atomicAdd(&red[c0 + 2], dg[i].z); atomicAdd(&red[c0 + 3], dg[i].w);
       }
+      if (dbeta) {
+        atomicAdd(&red[C + c0], db[i].x); atomicAdd(&red[C + c0 + 1], db[i].y);
+        atomicAdd(&red[C + c0 + 2], db[i].z); atomicAdd(&red[C + c0 + 3], db[i].w);
+      }
+      if (dx_colsum) {
+        atomicAdd(&red[2 * C + c0], ds[i].x); atomicAdd(&red[2 * C + c0 + 1], ds[i].y);
+        atomicAdd(&red[2 * C + c0 + 2], ds[i].z); atomicAdd(&red[2 * C + c0 + 3], ds[i].w);
+      }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      if (dgamma) atomicAdd(dgamma + c, red[c]);
+      if (dbeta) atomicAdd(dbeta + c, red[C + c]);
+      if (dx_colsum) atomicAdd(dx_colsum + c, red[2 * C + c]);
     }
   }
 }
@@ -520,7 +526,7 @@ extern "C" int pg_layernorm_bwd(const void* dy_bf16, const float* dy_f32, const 
   const bool fast = (C % 128 == 0) && C <= 1024;
   bf16* dxb = reinterpret_cast<bf16*>(dx_bf16);
   if (fast) {
-    const int blocks = grid_for((long long)P * 32, threads, 4);
+    const int blocks = grid_for((long long)P * 32, threads, 2);  // 128 registers: two resident blocks per SM
     switch (C / 128) {
 #define LNB_CASE(V)                                                                                              \
   case V:                                                                                                        \

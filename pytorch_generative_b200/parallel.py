@@ -36,21 +36,28 @@ class FlatGradAverager:
 
     @torch.no_grad()
     def average_(self):
-        """In place: p.grad <- mean over ranks of p.grad (parameters without a gradient contribute zeros)."""
+        """In place: p.grad <- mean over ranks of p.grad (parameters without a gradient contribute zeros).
+
+        Packing and unpacking are multi-tensor copies (a few launches for the whole bucket, not two per parameter);
+        NCCL averages inside the collective, other backends sum and the bucket is scaled afterwards."""
         if self.world == 1:
             return
+        have = [(p, v) for p, v in zip(self.params, self.views) if p.grad is not None]
         for p, v in zip(self.params, self.views):
             if p.grad is None:
                 v.zero_()
-            else:
-                v.copy_(p.grad)
-        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
-        self.flat.div_(self.world)
+        if have:
+            torch._foreach_copy_([v for _, v in have], [p.grad for p, _ in have])
+        if dist.get_backend() == "nccl":
+            dist.all_reduce(self.flat, op=dist.ReduceOp.AVG)
+        else:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+            self.flat.div_(self.world)
+        if have:
+            torch._foreach_copy_([p.grad for p, _ in have], [v for _, v in have])
         for p, v in zip(self.params, self.views):
             if p.grad is None:
                 p.grad = v.clone()
-            else:
-                p.grad.copy_(v)
 
 
 def shard_seed(base_seed, rank):
