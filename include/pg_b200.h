@@ -33,7 +33,12 @@ int pg_sm_count(void);
 unsigned long long pg_launch_count(void);
 
 /* Activation ids (shared by the GEMM epilogue and the elementwise kernels). */
-enum { PG_ACT_NONE = 0, PG_ACT_RELU = 1, PG_ACT_GELU = 2, PG_ACT_ELU = 3, PG_ACT_TANH = 4 };
+enum { PG_ACT_NONE = 0, PG_ACT_RELU = 1, PG_ACT_GELU = 2, PG_ACT_ELU = 3, PG_ACT_TANH = 4,
+       /* pg_gemm_epilogue.dact only: `aux` already holds the derivative (see PG_ACT_STORE_DERIV) */
+       PG_ACT_GIVEN = 5 };
+/* OR-ed into pg_gemm_epilogue.act: out_pre receives act'(pre) instead of pre, so that the matching dgrad epilogue
+ * (dact = PG_ACT_GIVEN) is a single multiply. */
+#define PG_ACT_STORE_DERIV 0x100
 
 /* ---------------------------------------------------------------------------------------------
  * Channel contraction (every nn.Conv2d 1x1 on the path and, per live tap, every masked conv):
@@ -59,11 +64,11 @@ enum { PG_ACT_NONE = 0, PG_ACT_RELU = 1, PG_ACT_GELU = 2, PG_ACT_ELU = 3, PG_ACT
  * ------------------------------------------------------------------------------------------- */
 typedef struct pg_gemm_epilogue {
   const float* bias;   /* [N] or NULL */
-  const void* aux;     /* bf16 [M,N] pre-activation, used when dact != 0 */
+  const void* aux;     /* bf16 [M,N] pre-activation (or the derivative itself, dact = PG_ACT_GIVEN), used when dact != 0 */
   const float* res0;   /* fp32 [M,N] or NULL */
   const float* res1;   /* fp32 [M,N] or NULL */
   void* out_bf16;      /* bf16 [M,N] or NULL */
-  void* out_pre;       /* bf16 [M,N] or NULL */
+  void* out_pre;       /* bf16 [M,N] or NULL: pre-activation (act'(pre) with PG_ACT_STORE_DERIV) */
   float* out_f32;      /* fp32 [M,N] or NULL */
   int64_t ld_aux, ld_res, ld_out_bf16, ld_out_pre, ld_out_f32; /* row pitches, elements */
   int32_t act;         /* activation applied to out_bf16 */

@@ -18,6 +18,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PG_B200_LIB") or os.path.join(_HERE, "libpg_b200.so")
 
 ACT_NONE, ACT_RELU, ACT_GELU, ACT_ELU, ACT_TANH = 0, 1, 2, 3, 4
+ACT_GIVEN = 5  # dact only: aux already holds the derivative
+ACT_STORE_DERIV = 0x100  # OR-ed into act: out_pre receives act'(pre)
 ACT_BY_NAME = {None: ACT_NONE, "none": ACT_NONE, "relu": ACT_RELU, "gelu": ACT_GELU, "elu": ACT_ELU, "tanh": ACT_TANH}
 
 _vp, _i32, _i64, _f32 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float

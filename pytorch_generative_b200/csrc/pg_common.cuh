@@ -403,6 +403,7 @@ __device__ __forceinline__ float pg_act_bwd(int act, float x) {
       float t = tanhf(x);
       return 1.f - t * t;
     }
+    case PG_ACT_GIVEN: return x;  // the operand already is the derivative
     default: return 1.f;
   }
 }

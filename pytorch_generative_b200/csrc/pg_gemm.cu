@@ -44,6 +44,7 @@ struct GemmParams {
   int vec_ok;       // all epilogue pointers/pitches allow 16-byte vector access (direct path)
   // staged (TMA) epilogue plan
   int staged;
+  int store_deriv;  // out_pre receives act'(pre) (PG_ACT_STORE_DERIV)
   int epi_depth;    // staging stages per epilogue warpgroup (1 or 2)
   int epi_stage_bytes;
   int off_res0, off_res1, off_aux, off_outf, off_outb, off_outp;  // slab offsets inside an epilogue stage, -1 = absent
@@ -123,14 +124,17 @@ __device__ __forceinline__ void epilogue_row32(const GemmParams& p, int row, int
   }
   if (e.out_pre) {
     bf16* o = reinterpret_cast<bf16*>(e.out_pre) + (size_t)row * e.ld_out_pre + col0;
+    float d[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) d[i] = p.store_deriv ? pg_act_bwd(e.act, v[i]) : v[i];
     if (full) {
 #pragma unroll
       for (int i = 0; i < 4; ++i)
         reinterpret_cast<uint4*>(o)[i] =
-            make_uint4(pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
-                       pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
+            make_uint4(pack_bf16x2(d[8 * i], d[8 * i + 1]), pack_bf16x2(d[8 * i + 2], d[8 * i + 3]),
+                       pack_bf16x2(d[8 * i + 4], d[8 * i + 5]), pack_bf16x2(d[8 * i + 6], d[8 * i + 7]));
     } else {
-      for (int i = 0; i < ncols; ++i) o[i] = __float2bfloat16(v[i]);
+      for (int i = 0; i < ncols; ++i) o[i] = __float2bfloat16(d[i]);
     }
   }
   if (e.out_bf16) {
@@ -440,7 +444,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (p.off_aux >= 0) {
           float x[32];
           slab_bf16_load(base + p.off_aux, r, x);
-          if (e.dact == PG_ACT_GELU) {
+          if (e.dact == PG_ACT_GIVEN) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] *= x[i];
+          } else if (e.dact == PG_ACT_GELU) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] *= pg_act_bwd(PG_ACT_GELU, x[i]);
           } else {
@@ -458,7 +465,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         __syncwarp();  // bar.sync / tcgen05.ld are warp-aligned: reconverge after every leader-only section
         asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
         if (p.off_outf >= 0) slab_f32_store(base + p.off_outf, r, v);
-        if (p.off_outp >= 0) slab_bf16_store(base + p.off_outp, r, v);
+        if (p.off_outp >= 0) {
+          if (p.store_deriv) {  // act'(pre); shares the tanh of the activation below
+            float d[32];
+            if (e.act == PG_ACT_GELU) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) d[i] = pg_act_bwd(PG_ACT_GELU, v[i]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) d[i] = pg_act_bwd(e.act, v[i]);
+            }
+            slab_bf16_store(base + p.off_outp, r, d);
+          } else {
+            slab_bf16_store(base + p.off_outp, r, v);
+          }
+        }
         if (p.off_outb >= 0) {
           if (e.act == PG_ACT_GELU) {
 #pragma unroll
@@ -596,7 +617,9 @@ gemm_skinny_kernel(const bf16* __restrict__ A, int64_t lda, const bf16* __restri
     if (e.res0) t += e.res0[(size_t)m * e.ld_res + n];
     if (e.res1) t += e.res1[(size_t)m * e.ld_res + n];
     if (e.out_f32) e.out_f32[(size_t)m * e.ld_out_f32 + n] = t;
-    if (e.out_pre) reinterpret_cast<bf16*>(e.out_pre)[(size_t)m * e.ld_out_pre + n] = __float2bfloat16(t);
+    if (e.out_pre)
+      reinterpret_cast<bf16*>(e.out_pre)[(size_t)m * e.ld_out_pre + n] =
+          __float2bfloat16(p.store_deriv ? pg_act_bwd(e.act, t) : t);
     if (e.out_bf16) reinterpret_cast<bf16*>(e.out_bf16)[(size_t)m * e.ld_out_bf16 + n] = __float2bfloat16(pg_act_fwd(e.act, t));
   }
 }
@@ -755,6 +778,9 @@ extern "C" int pg_gemm_bf16(const void* A, int a_mn_major, int64_t lda, const vo
   p.k_per_split = (p.k_iters + split_k - 1) / split_k;
   p.splits = (p.k_iters + p.k_per_split - 1) / p.k_per_split;  // no empty split
   p.epi = *epi;
+  p.store_deriv = (epi->act & PG_ACT_STORE_DERIV) ? 1 : 0;
+  p.epi.act = epi->act & 0xff;
+  PG_REQUIRE(!p.store_deriv || epi->out_pre, "pg_gemm_bf16: PG_ACT_STORE_DERIV needs out_pre");
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   p.vec_ok = 1;
   if (epi->bias && !al16(epi->bias)) p.vec_ok = 0;

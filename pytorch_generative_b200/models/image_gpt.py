@@ -88,7 +88,7 @@ class _ImageGPTStack(torch.autograd.Function):
             _, _, hres = ops.linear_fwd(o, wp, p_b.detach(), res0=xs, want_bf16=False, want_f32=True)
             a2, _, mean2, rstd2 = ops.layernorm_fwd(hres, ln2_w.detach(), ln2_b.detach(), eps)
             w1, w2 = ops.pack_weight(f1_w), ops.pack_weight(f2_w)
-            g, u, _ = ops.linear_fwd(a2, w1, f1_b.detach(), act=L.ACT_GELU, want_pre=True)
+            g, u, _ = ops.linear_fwd(a2, w1, f1_b.detach(), act=L.ACT_GELU, want_pre=True, pre_deriv=True)  # u = GELU'(pre)
             _, _, xs_new = ops.linear_fwd(g, w2, f2_b.detach(), res0=xs, res1=hres, want_bf16=False, want_f32=True)
             if keep:
                 saved.append(dict(xs=xs, a1=a1, qkv=qkv, o=o, lse=lse, h=hres, a2=a2, u=u, g=g, mean1=mean1, rstd1=rstd1,
@@ -149,7 +149,7 @@ class _ImageGPTStack(torch.autograd.Function):
             dw2 = carve(b, 0, C, 4 * C)
             ops.linear_wgrad(dx_b, blk["g"], dw2)
             grads[base_i + 12] = dw2.view(C, 4 * C, 1, 1)
-            du = ops.linear_dgrad(dx_b, blk["w2"], aux=blk["u"], dact=L.ACT_GELU)
+            du = ops.linear_dgrad(dx_b, blk["w2"], aux=blk["u"], dact=L.ACT_GIVEN)
             grads[base_i + 11] = ops.bias_grad(du)
             dw1 = carve(b, 4 * C * C, 4 * C, C)
             ops.linear_wgrad(du, blk["a2"], dw1)

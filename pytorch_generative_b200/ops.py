@@ -82,15 +82,17 @@ def pm_to_nchw(x_pm, n, c, h, w, act=L.ACT_NONE):
 # Linear (1x1 conv) forward / dgrad / wgrad on pixel-major activations
 # --------------------------------------------------------------------------------------------------
 def linear_fwd(a, w, bias=None, *, act=L.ACT_NONE, res0=None, res1=None, want_bf16=True, want_pre=False,
-               want_f32=False, n_out=None, skinny=False):
+               want_f32=False, n_out=None, skinny=False, pre_deriv=False):
     """y = a @ w.T (+bias) (+res0 +res1).  a: [P, K] bf16, w: [Cout, K] bf16.
-    Returns (out_bf16 = act(pre), out_pre = bf16(pre), out_f32 = pre), each None unless requested."""
+    Returns (out_bf16 = act(pre), out_pre = bf16(pre), out_f32 = pre), each None unless requested.
+    pre_deriv: out_pre holds act'(pre) instead (consumed by linear_dgrad(dact=L.ACT_GIVEN))."""
     P, K = a.shape
     n = n_out or w.shape[0]
     ob = empty((P, n), BF16, a) if want_bf16 else None
     op = empty((P, n), BF16, a) if want_pre else None
     of = empty((P, n), F32, a) if want_f32 else None
-    L.gemm(a, w, P, n, K, bias=bias, res0=res0, res1=res1, out_bf16=ob, out_pre=op, out_f32=of, act=act,
+    L.gemm(a, w, P, n, K, bias=bias, res0=res0, res1=res1, out_bf16=ob, out_pre=op, out_f32=of,
+           act=(act | L.ACT_STORE_DERIV) if (pre_deriv and want_pre) else act,
            impl=2 if (skinny and P <= 32) else GEMM_IMPL)
     return ob, op, of
 

@@ -156,6 +156,27 @@ def test_gemm_epilogue_dact(L, impl, M):
     assert_close("dact", out, acc * _dgelu(u.float()), rtol=2 ** -8)
 
 
+@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("M", [640, 19200])
+def test_gemm_stored_derivative(L, impl, M):
+    """FC1 forward stores gelu'(pre) (PG_ACT_STORE_DERIV); the FC2 dgrad epilogue multiplies by it (PG_ACT_GIVEN)."""
+    N, K = 512, 256
+    A, B, acc = _operands(M, N, K, False, False, seed=11)
+    bias = torch.randn(N, generator=torch.Generator().manual_seed(12)).to(_dev())
+    out_d = torch.empty(M, N, device=_dev(), dtype=torch.bfloat16)
+    out_b = torch.empty(M, N, device=_dev(), dtype=torch.bfloat16)
+    L.gemm(A, B, M, N, K, bias=bias, out_pre=out_d, out_bf16=out_b, act=L.ACT_GELU | L.ACT_STORE_DERIV, impl=impl)
+    torch.cuda.synchronize()
+    pre = acc + bias
+    assert_close("gelu", out_b, _gelu(pre), rtol=2 ** -8)
+    assert_close("gelu'", out_d, _dgelu(pre), rtol=2 ** -8, atol=2e-3)
+    A2, B2, acc2 = _operands(M, N, K, False, True, seed=13)
+    out = torch.empty(M, N, device=_dev(), dtype=torch.bfloat16)
+    L.gemm(A2, B2, M, N, K, b_mn=True, aux=out_d, dact=L.ACT_GIVEN, out_bf16=out, impl=impl)
+    torch.cuda.synchronize()
+    assert_close("given", out, acc2 * out_d.float(), rtol=2 ** -8)
+
+
 @pytest.mark.parametrize("split_k", [1, 3, 8])
 def test_gemm_wgrad_splitk_accumulate(L, split_k):
     """wgrad shape: dW[Cout,Cin] += dYᵀ·X over P pixels, split along the pixel dimension with fp32 atomics."""

@@ -50,11 +50,13 @@ def case(name, M, N, K, **kw):
 case("qkv fwd (bias)", P, 1536, 512, bias=True)
 case("proj fwd (bias,res->f32)", P, 512, 512, bias=True, res=True, f32=True, f32_only=True)
 case("fc1 fwd (bias,gelu,pre)", P, 2048, 512, bias=True, act=L.ACT_GELU, pre=True)
+case("fc1 fwd (bias,gelu,gelu')", P, 2048, 512, bias=True, act=L.ACT_GELU | L.ACT_STORE_DERIV, pre=True)
 case("fc2 fwd (bias,2res->f32)", P, 512, 2048, bias=True, res=True, res2=True, f32=True, f32_only=True)
 case("plain 512x512", P, 512, 512)
 case("plain 2048x512", P, 2048, 512)
 # dgrad (B MN-major)
 case("fc2 dgrad (dgelu)", P, 2048, 512, b_mn=True, dact=L.ACT_GELU)
+case("fc2 dgrad (given gelu')", P, 2048, 512, b_mn=True, dact=L.ACT_GIVEN)
 case("fc1 dgrad", P, 512, 2048, b_mn=True)
 case("qkv dgrad", P, 512, 1536, b_mn=True)
 # wgrad (MN,MN), split-K over pixels
