@@ -384,6 +384,17 @@ __device__ __forceinline__ float pg_act_fwd(int act, float x) {
     default: return x;
   }
 }
+// GELU and its derivative from one tanh (the forward epilogue that also stores act'(pre), PG_ACT_STORE_DERIV)
+__device__ __forceinline__ void pg_gelu_both(float x, float& g, float& d) {
+  const float xc = fminf(fmaxf(x, -8.f), 8.f);
+  const float x2 = xc * xc;
+  const float q = xc * fmaf(x2, fmaf(x2, -0.0003563930330798993f, 0.037032072878891306f), 0.7974856909542073f);
+  const float qp = fmaf(x2, fmaf(x2, -0.0017819651653994965f, 0.11109621863667392f), 0.7974856909542073f);
+  const float t = pg_tanh_fast(q);
+  const float hx = 0.5f * x;
+  g = fmaf(hx, t, hx);
+  d = fmaf(xc * qp, fmaf(-0.5f * t, t, 0.5f), fmaf(0.5f, t, 0.5f));
+}
 // derivative w.r.t. the pre-activation x
 __device__ __forceinline__ float pg_act_bwd(int act, float x) {
   switch (act) {

@@ -465,33 +465,37 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         __syncwarp();  // bar.sync / tcgen05.ld are warp-aligned: reconverge after every leader-only section
         asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
         if (p.off_outf >= 0) slab_f32_store(base + p.off_outf, r, v);
-        if (p.off_outp >= 0) {
-          if (p.store_deriv) {  // act'(pre); shares the tanh of the activation below
-            float d[32];
-            if (e.act == PG_ACT_GELU) {
+        if (p.store_deriv && e.act == PG_ACT_GELU && p.off_outp >= 0 && p.off_outb >= 0) {
+          // MLP forward: GELU(pre) and GELU'(pre) from one tanh per element
+          float d[32];
 #pragma unroll
-              for (int i = 0; i < 32; ++i) d[i] = pg_act_bwd(PG_ACT_GELU, v[i]);
-            } else {
+          for (int i = 0; i < 32; ++i) pg_gelu_both(v[i], v[i], d[i]);
+          slab_bf16_store(base + p.off_outp, r, d);
+          slab_bf16_store(base + p.off_outb, r, v);
+        } else {
+          if (p.off_outp >= 0) {
+            if (p.store_deriv) {
+              float d[32];
 #pragma unroll
               for (int i = 0; i < 32; ++i) d[i] = pg_act_bwd(e.act, v[i]);
+              slab_bf16_store(base + p.off_outp, r, d);
+            } else {
+              slab_bf16_store(base + p.off_outp, r, v);
             }
-            slab_bf16_store(base + p.off_outp, r, d);
-          } else {
-            slab_bf16_store(base + p.off_outp, r, v);
           }
-        }
-        if (p.off_outb >= 0) {
-          if (e.act == PG_ACT_GELU) {
+          if (p.off_outb >= 0) {
+            if (e.act == PG_ACT_GELU) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = pg_act_fwd(PG_ACT_GELU, v[i]);
-          } else if (e.act == PG_ACT_RELU) {
+              for (int i = 0; i < 32; ++i) v[i] = pg_act_fwd(PG_ACT_GELU, v[i]);
+            } else if (e.act == PG_ACT_RELU) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
-          } else if (e.act != PG_ACT_NONE) {
+              for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+            } else if (e.act != PG_ACT_NONE) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = pg_act_fwd(e.act, v[i]);
+              for (int i = 0; i < 32; ++i) v[i] = pg_act_fwd(e.act, v[i]);
+            }
+            slab_bf16_store(base + p.off_outb, r, v);
           }
-          slab_bf16_store(base + p.off_outb, r, v);
         }
         fence_proxy_async_smem();
         asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
