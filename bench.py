@@ -159,7 +159,9 @@ def run_ours(args):
     train_model = model
     parallel.broadcast_parameters(model)       # rank 0's weights everywhere (what DDP does at construction)
     params = [p for p in model.parameters()]
-    grad_avg = parallel.FlatGradAverager(params)  # one flat NCCL all-reduce per step; no-op at world size 1
+    # block-bucketed all-reduce overlapped with backward (ImageGPT) + one flat bucket for the rest; no-op at world size 1
+    grad_avg = parallel.OverlappedGradAverager(model, params) if os.environ.get("PG_DP_OVERLAP", "1") != "0" \
+        else parallel.FlatGradAverager(params)
     opt = torch.optim.Adam(params, lr=spec["lr"])
     sched = torch.optim.lr_scheduler.MultiplicativeLR(opt, lr_lambda=lambda _: 0.999977)
     x_host = synthetic_batch(batch, spec["shape"], seed=parallel.shard_seed(0, rank)).pin_memory()  # rank r: seed r

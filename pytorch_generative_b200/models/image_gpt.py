@@ -139,6 +139,11 @@ class _ImageGPTStack(torch.autograd.Function):
             start = b * per_block + off
             return arena[start: start + rows * cols].view(rows, cols)
 
+        # data parallelism: each block's slice of the arena is handed to the bucket hook (an asynchronous all-reduce)
+        # as soon as its last wgrad GEMM is queued; see parallel.OverlappedGradAverager
+        bucket_hook = _ImageGPTStack.grad_bucket_hook if _arena_views_are_grads(sv) else None
+        pending = []
+
         for b in reversed(range(n_blocks)):
             blk = sv["blocks"][b]
             base_i = 3 + b * PARAMS_PER_BLOCK
@@ -191,6 +196,8 @@ class _ImageGPTStack(torch.autograd.Function):
             dx, dx_b, grads[base_i + 0], grads[base_i + 1], dx_sum = ops.layernorm_bwd(
                 da1, blk["xs"], ln1_w.detach(), blk["mean1"], blk["rstd1"], dres0=dx, dres1=dh, want_colsum=True)
             del da1, dh, dh_b
+            if bucket_hook is not None:
+                pending.append(bucket_hook(arena[b * per_block: (b + 1) * per_block]))
             sv["blocks"][b] = None  # release this block's activations
 
         in_w = params[1]
@@ -204,7 +211,18 @@ class _ImageGPTStack(torch.autograd.Function):
         dpos[:, :, : h, : w] = dx_in.sum(dim=0, keepdim=True)
         grads[0] = dpos
         ctx.saved = None
+        for handle in pending:  # the gradients leave this node averaged
+            handle.wait()
         return (dx_in if ctx.needs_input_grad[0] else None, None, None, *grads)
+
+
+def _arena_views_are_grads(sv):
+    """True when every block's weight gradients are plain views of the gradient arena (heads fill their 64-wide
+    slots, e.g. 512 channels / 8 heads): only then can the arena slice be averaged in place."""
+    return bool(sv["blocks"]) and all(blk["meta"]["identity"] for blk in sv["blocks"])
+
+
+_ImageGPTStack.grad_bucket_hook = None  # set through ImageGPT.set_grad_bucket_hook (process-wide: one model per rank)
 
 
 class ImageGPT(base.AutoregressiveModel):
@@ -343,6 +361,23 @@ class ImageGPT(base.AutoregressiveModel):
                 canvas[:, :, row, col] = new
                 xin[:, :, row + ph, col + pw] = new + pos_emb[0, :, row, col]
         return canvas
+
+    # ---- data-parallel bucket protocol (parallel.OverlappedGradAverager) ----
+    def set_grad_bucket_hook(self, fn):
+        """fn(flat_fp32_bucket) -> handle with wait(); called once per transformer block during backward."""
+        _ImageGPTStack.grad_bucket_hook = fn
+
+    def bucketed_parameters(self):
+        """Parameters whose gradients are averaged by the bucket hook (the block weight matrices), or [] when the
+        head geometry needs slot padding (their gradients are then gathered copies, averaged by the flat bucket)."""
+        c = self._ln.weight.numel()
+        if c // self._n_heads != ops.HEAD_SLOT:
+            return []
+        out = []
+        for blk in self._transformer:
+            a = blk._attn
+            out += [a._q.weight, a._kv.weight, a._proj.weight, blk._out[0].weight, blk._out[2].weight]
+        return out
 
     def forward(self, x):
         if not x.is_cuda:

@@ -86,3 +86,31 @@ def test_sample_argument_contract():
         m.sample()  # neither n_samples nor conditioned_on (reference base.py:87-89)
     with pytest.raises(AttributeError):
         m.sample(n_samples=1)  # before any forward: shape buffers do not exist yet, as in the reference
+
+
+def test_overlay_rebinds_reference_names():
+    """overlay.install() makes the reference package hand out the B200 classes (and uninstall() restores it)."""
+    import os
+    import sys
+
+    if not os.path.isdir("/root/reference/pytorch_generative"):
+        pytest.skip("reference checkout not present")
+    sys.path.insert(0, "/root/reference")
+    try:
+        import pytorch_generative as ref
+
+        from pytorch_generative_b200 import models, nn, overlay
+
+        orig = ref.models.ImageGPT
+        bound = overlay.install()
+        try:
+            assert ref.models.ImageGPT is models.ImageGPT and ref.nn.CausalAttention is nn.CausalAttention
+            assert ref.models.autoregressive.pixel_snail.PixelSNAIL is models.PixelSNAIL
+            assert len(bound) == 5 + 2 * 4
+            m = ref.models.PixelCNN(in_channels=1, out_channels=1, n_residual=1, residual_channels=4, head_channels=4)
+            assert isinstance(m, models.PixelCNN)
+        finally:
+            overlay.uninstall()
+        assert ref.models.ImageGPT is orig
+    finally:
+        sys.path.remove("/root/reference")

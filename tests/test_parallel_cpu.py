@@ -45,3 +45,80 @@ def test_flat_gradient_average_matches_mean_over_ranks(tmp_path):
     for i in range(len(r[0]["avg"])):
         want = (r[0]["local"][i] + r[1]["local"][i]) / 2
         assert torch.allclose(r[0]["avg"][i], want, atol=1e-6) and torch.equal(r[0]["avg"][i], r[1]["avg"][i])
+
+
+class _ArenaFn(torch.autograd.Function):
+    """Stand-in for the fused ImageGPT stack: both weight gradients are views of one arena, handed to the bucket hook
+    per 'block' inside backward (same protocol as models/image_gpt.py)."""
+
+    hook = None
+
+    @staticmethod
+    def forward(ctx, x, w0, w1, b):
+        ctx.save_for_backward(x, w0, w1)
+        return torch.tanh(x @ w0.t()) @ w1.t() + b
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w0, w1 = ctx.saved_tensors
+        h = torch.tanh(x @ w0.t())
+        arena = torch.zeros(w0.numel() + w1.numel())
+        dw1 = arena[w0.numel():].view_as(w1)
+        dw1 += dy.t() @ h
+        pending = []
+        if _ArenaFn.hook is not None:
+            pending.append(_ArenaFn.hook(arena[w0.numel():]))
+        dh = (dy @ w1) * (1 - h * h)
+        dw0 = arena[: w0.numel()].view_as(w0)
+        dw0 += dh.t() @ x
+        if _ArenaFn.hook is not None:
+            pending.append(_ArenaFn.hook(arena[: w0.numel()]))
+        for hd in pending:
+            hd.wait()
+        return None, dw0, dw1, dy.sum(0)
+
+
+class _ArenaModel(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.w0 = torch.nn.Parameter(torch.randn(5, 6))
+        self.w1 = torch.nn.Parameter(torch.randn(3, 5))
+        self.b = torch.nn.Parameter(torch.randn(3))
+
+    def set_grad_bucket_hook(self, fn):
+        _ArenaFn.hook = fn
+
+    def bucketed_parameters(self):
+        return [self.w0, self.w1]
+
+    def forward(self, x):
+        return _ArenaFn.apply(x, self.w0, self.w1, self.b)
+
+
+def _overlap_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from pytorch_generative_b200 import parallel
+
+    torch.manual_seed(5)
+    model = _ArenaModel()
+    x = torch.randn(4, 6, generator=torch.Generator().manual_seed(parallel.shard_seed(11, rank)))
+    model(x).pow(2).sum().backward()  # no hook yet: local gradients
+    local = [p.grad.clone() for p in model.parameters()]
+    model.zero_grad(set_to_none=True)
+    avg = parallel.OverlappedGradAverager(model)
+    assert avg.n_bucketed == 2
+    model(x).pow(2).sum().backward()  # buckets averaged inside backward
+    avg.average_()                    # the bias through the flat bucket
+    torch.save({"local": local, "avg": [p.grad.clone() for p in model.parameters()]}, os.path.join(out_dir, f"o{rank}.pt"))
+    dist.destroy_process_group()
+
+
+def test_block_bucket_average_inside_backward(tmp_path):
+    world, port = 2, _free_port()
+    mp.spawn(_overlap_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    r = [torch.load(tmp_path / f"o{i}.pt") for i in range(world)]
+    for i in range(3):
+        want = (r[0]["local"][i] + r[1]["local"][i]) / 2
+        assert torch.allclose(r[0]["avg"][i], want, atol=1e-6), i
+        assert torch.equal(r[0]["avg"][i], r[1]["avg"][i])
