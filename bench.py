@@ -130,6 +130,21 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+class _stdout_to_stderr:
+    """Routes file descriptor 1 to stderr for the duration of the block (C libraries that write to stdout)."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self._saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self._saved, 1)
+        os.close(self._saved)
+        return False
+
+
 # --------------------------------------------------------------------------------------------------
 # Our arm
 # --------------------------------------------------------------------------------------------------
@@ -150,7 +165,9 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        with _stdout_to_stderr():  # NCCL prints its version banner on stdout; stdout carries the one JSON line only
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
     L.load()
 
     batch = args.batch or spec["batch"]
