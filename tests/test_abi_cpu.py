@@ -114,3 +114,40 @@ def test_overlay_rebinds_reference_names():
         assert ref.models.ImageGPT is orig
     finally:
         sys.path.remove("/root/reference")
+
+
+def test_ctypes_structs_and_signatures_match_the_header(tmp_path):
+    """The header is the contract: compile it with gcc (plain C, no CUDA), compare sizeof / offsetof of
+    pg_gemm_epilogue with the ctypes mirror, and the arity of every declared function with the Python binding."""
+    import ctypes
+    import shutil
+    import subprocess
+
+    from pytorch_generative_b200 import _lib
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    fields = [name for name, _ in _lib.GemmEpilogue._fields_]
+    prog = ['#include <stddef.h>', '#include <stdio.h>', '#include "pg_b200.h"', "int main(void) {",
+            '  printf("size %zu\\n", sizeof(pg_gemm_epilogue));']
+    prog += [f'  printf("{f} %zu\\n", offsetof(pg_gemm_epilogue, {f}));' for f in fields]
+    prog += ['  printf("acts %d %d %d\\n", PG_ACT_GELU, PG_ACT_GIVEN, PG_ACT_STORE_DERIV);', "  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(prog))
+    exe = tmp_path / "layout"
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)],
+                   check=True)
+    got = dict(line.split(" ", 1) for line in subprocess.run([str(exe)], capture_output=True, text=True,
+                                                             check=True).stdout.strip().splitlines())
+    assert int(got["size"]) == ctypes.sizeof(_lib.GemmEpilogue)
+    for f in fields:
+        assert int(got[f]) == getattr(_lib.GemmEpilogue, f).offset, f
+    assert got["acts"].split() == [str(_lib.ACT_GELU), str(_lib.ACT_GIVEN), str(_lib.ACT_STORE_DERIV)]
+
+    # arity of every prototype in the header == len(argtypes) of the binding
+    text = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "pg_b200.h")).read(), flags=re.S)
+    for name, args in re.findall(r"\b(pg_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", text):
+        n_args = 0 if args.strip() in ("", "void") else len(args.split(","))
+        if name in _lib._SIGNATURES:
+            assert len(_lib._SIGNATURES[name]) == n_args, (name, n_args, len(_lib._SIGNATURES[name]))
