@@ -362,7 +362,9 @@ def run_reference(args):
     cb = cpu_baseline(spec, steps=steps, warmup=1)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     out = {
-        "impl": "reference", "metric": "images/sec training step (ImageGPT CIFAR-10 32x32)", "value": cb["value"],
+        "impl": "reference",
+        "metric": "images/sec training step (ImageGPT CIFAR-10 32x32)" if args.config == "c5" else
+        f"images/sec training step ({spec['name']})", "value": cb["value"],
         "unit": "images/sec", "n_gpus": world, "steps": steps, "warmup": 1, "ms_per_step": cb["ms_per_step"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": spec["name"] + f", CPU batch {spec['cpu_batch']} (bounded sample)", "parallelism": "cpu"},
