@@ -112,3 +112,10 @@ class OverlappedGradAverager:
 def shard_seed(base_seed, rank):
     """Synthetic-data seed of a rank: every rank draws its own batch (weak scaling, like the reference's loaders)."""
     return int(base_seed) + int(rank)
+
+
+def shard_samples(n_samples, rank, world):
+    """`sample()` across GPUs is replicas only: rank r draws its share of the `n_samples` images, no
+    communication.  Returns the number of images rank `rank` generates (shares differ by at most one)."""
+    base, extra = divmod(int(n_samples), int(world))
+    return base + (1 if rank < extra else 0)

@@ -122,3 +122,12 @@ def test_block_bucket_average_inside_backward(tmp_path):
         want = (r[0]["local"][i] + r[1]["local"][i]) / 2
         assert torch.allclose(r[0]["avg"][i], want, atol=1e-6), i
         assert torch.equal(r[0]["avg"][i], r[1]["avg"][i])
+
+
+def test_sample_sharding_is_balanced_and_complete():
+    from pytorch_generative_b200 import parallel
+
+    for n in (0, 1, 7, 16, 17):
+        for world in (1, 2, 8):
+            shares = [parallel.shard_samples(n, r, world) for r in range(world)]
+            assert sum(shares) == n and max(shares) - min(shares) <= 1
