@@ -145,7 +145,8 @@ int pg_cast_f32_to_bf16(const float* x, void* y, int64_t numel, void* stream);
  * that head slots may be zero-padded: the tcgen05 kernels require dk == 64 and dv in {64, 128}, narrower
  * heads are laid out in 64-wide slots whose extra columns are zero).
  * lse [N, H, S] fp32 (log-sum-exp of scaled scores; rows without keys store 0 and o = 0).
- * impl: 0 = tcgen05 kernel, 1 = SIMT cross-check (any dk, dv <= 128, S <= 1024).
+ * impl: 0 = tcgen05 kernel, 1 = SIMT cross-check (any dk, dv <= 128, S <= 1024); backward only: 2 = experimental
+ * split-phase tcgen05 kernel (dv slot 64), opt-in, never selected by the product.
  * ------------------------------------------------------------------------------------------- */
 int pg_causal_attn_fwd(const void* q, int64_t ld_q, const void* k, int64_t ld_k, const void* v, int64_t ld_v,
                        void* o, int64_t ld_o, float* lse, int N, int S, int H, int dk, int dv, float scale,

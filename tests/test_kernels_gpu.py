@@ -4,6 +4,7 @@ tolerance: fp32 accumulation of bf16 products must match an fp32 matmul of the s
 ~1e-5 relative (summation order only); bf16 outputs to one bf16 ulp (2^-8 relative)."""
 
 import math
+import os
 
 import pytest
 import torch
@@ -446,6 +447,31 @@ def test_attention_fwd_bwd(L, case, impl):
     assert_close("attn dv", _from_slots(dv_, H, dv, vs), dv_ref, rtol=2 ** -6, atol=2e-3)
     if impl == 0 and dk < ks:
         assert (dq.reshape(P, H, ks)[:, :, dk:] == 0).all() and (dk_.reshape(P, H, ks)[:, :, dk:] == 0).all()
+
+
+@pytest.mark.skipif(os.environ.get("PG_TEST_EXPERIMENTAL") != "1",
+                    reason="experimental split-phase attention backward (impl 2): opt-in, not the product path")
+@pytest.mark.parametrize("case", [c for c in ATTN_CASES if c[4] <= 64])
+def test_attention_bwd_split_experimental(L, case):
+    """impl = 2 of pg_causal_attn_bwd against the torch reference (forward through the product kernel)."""
+    N, S, H, dk, dv, strict = case
+    q, k, v, do = _attn_inputs(N, S, H, dk, dv)
+    P = N * S
+    o_ref, lse_ref, dq_ref, dk_ref, dv_ref = _attn_ref(q, k, v, do, N, S, H, dk, dv, strict)
+    q, k, v, do = _to_slots(q, H, dk, 64), _to_slots(k, H, dk, 64), _to_slots(v, H, dv, 64), _to_slots(do, H, dv, 64)
+    o = torch.empty(P, H * 64, device=_dev(), dtype=torch.bfloat16)
+    lse = torch.empty(N, H, S, device=_dev())
+    L.causal_attn_fwd(q, k, v, o, lse, N, S, H, 64, 64, strict, impl=0, dk_true=dk)
+    dq = torch.full((P, H * 64), float("nan"), device=_dev(), dtype=torch.bfloat16)
+    dk_ = torch.full((P, H * 64), float("nan"), device=_dev(), dtype=torch.bfloat16)
+    dv_ = torch.full((P, H * 64), float("nan"), device=_dev(), dtype=torch.bfloat16)
+    delta = torch.empty(N, H, S, device=_dev())
+    dq_acc = torch.zeros(P, H * 64, device=_dev())
+    L.causal_attn_bwd(q, k, v, o, do, lse, delta, dq_acc, dq, dk_, dv_, N, S, H, 64, 64, strict, impl=2, dk_true=dk)
+    torch.cuda.synchronize()
+    assert_close("attn dq", _from_slots(dq, H, dk, 64), dq_ref, rtol=2 ** -6, atol=2e-3)
+    assert_close("attn dk", _from_slots(dk_, H, dk, 64), dk_ref, rtol=2 ** -6, atol=2e-3)
+    assert_close("attn dv", _from_slots(dv_, H, dv, 64), dv_ref, rtol=2 ** -6, atol=2e-3)
 
 
 # --------------------------------------------------------------------------------------------------
