@@ -109,9 +109,16 @@ def linear_dgrad(dy, w, *, aux=None, dact=L.ACT_NONE, want_f32=False, k_in=None)
 
 
 def _split_k_for(m_out, n_out, k):
+    """Split-K factor of a wgrad GEMM: the largest one whose work items (output tiles x splits) still fit ONE wave of
+    the persistent grid.  Rounding up instead (e.g. 32 tiles x 5 = 160 items on 148 SMs) makes a few CTAs run two
+    items back to back, so the launch lasts two split-lengths: 2 x 205 k-iterations instead of 1 x 256 at the C5 MLP
+    shapes (measured: split 4 and split 8 of that GEMM take the same 114-119 us, profiles/r01_gemm_microbench_final.txt)."""
     tiles = ((m_out + 127) // 128) * ((n_out + 255) // 256)
     sms = L.sm_count()
-    want = max(1, (sms + tiles - 1) // tiles)
+    if os.environ.get("PG_SPLITK_ROUND_UP") == "1":  # previous heuristic, kept for A/B runs
+        want = max(1, (sms + tiles - 1) // tiles)
+    else:
+        want = max(1, sms // tiles)
     k_iters = (k + 63) // 64
     return max(1, min(want, k_iters // 8 if k_iters >= 16 else 1))
 
