@@ -7,7 +7,7 @@
 //
 // impl 1 (this section): SIMT kernels, one warp per row — the on-device cross-check used by the tests.
 // impl 0: tensor-core kernels (pg_attention_tc.cuh), the product path.
-// impl 2 (backward only): experimental split-phase tensor-core kernel (pg_attention_tc_split.cuh), opt-in.
+// impl 3 (backward only): the round-1 tensor-core kernel (one CTA per key tile), kept for A/B measurements.
 #include <type_traits>
 
 #include "../../include/pg_b200.h"
@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const DecodeArgs a) {
 }  // namespace
 
 #include "pg_attention_tc.cuh"
-#include "pg_attention_tc_split.cuh"
+#include "pg_attention_bwd2.cuh"
 
 extern "C" int pg_causal_attn_fwd(const void* q, int64_t ld_q, const void* k, int64_t ld_k, const void* v,
                                   int64_t ld_v, void* o, int64_t ld_o, float* lse, int N, int S, int H, int dk,
@@ -345,8 +345,8 @@ extern "C" int pg_causal_attn_bwd(const void* q, int64_t ld_q, const void* k, in
     attn_bwd_dkv_simt<<<(unsigned)((total + 3) / 4), 128, smem_kv, stream>>>(a);
     return pg_check_launch("pg_causal_attn_bwd(dkv simt)");
   }
-  if (impl == 2) return attn_bwd_tc_split(a, stream);  // experimental split-phase kernel, never the default
-  return attn_bwd_tc(a, stream);
+  if (impl == 3) return attn_bwd_tc(a, stream);  // round-1 kernel (one CTA per key tile), kept for A/B measurements
+  return attn_bwd_tc2(a, stream);            // persistent, stage-pipelined kernel
 }
 
 extern "C" int pg_attn_decode(const void* q, int64_t ld_q, const void* k_new, int64_t ld_kn, const void* v_new, int64_t ld_vn,

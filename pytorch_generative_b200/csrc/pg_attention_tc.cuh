@@ -42,6 +42,22 @@ __device__ __forceinline__ void store_tile_row_chunk(uint8_t* tile, int r, int c
   }
 }
 
+// 16 consecutive elements (sub-chunk c16 of 8) of row r, given as 8 packed bf16x2 words.
+__device__ __forceinline__ void store_tile_row_16(uint8_t* tile, int r, int c16, const uint32_t (&w)[8]) {
+  uint8_t* row = tile + (c16 >> 2) * ATOM_BYTES + r * 128;
+  const int unit0 = (c16 & 3) * 2;
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int uidx = (unit0 + u) ^ (r & 7);
+    *reinterpret_cast<uint4*>(row + uidx * 16) = make_uint4(w[4 * u], w[4 * u + 1], w[4 * u + 2], w[4 * u + 3]);
+  }
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+
 // Descriptors for the two views of a tile whose atoms are ATOM_BYTES apart.
 // K-major view: K runs along the 64 columns of an atom (then to the next atom); kk = index of the 16-wide K step.
 __device__ __forceinline__ uint64_t desc_kmajor(uint32_t tile_addr, int kk) {
@@ -188,21 +204,40 @@ attn_fwd_tc_kernel(const __grid_constant__ AttnTmaps tm, const AttnArgs a, const
       const int k0 = j * AT;
       float mx = m, lt = 0.f, alpha = 1.f;
       // One score tile: running max, then P = exp2(s * c - m * c) to smem.  MASK is a compile-time flag so that only
-      // the diagonal tile pays for the per-element causal compare / select.
+      // the diagonal tile pays for the per-element causal compare / select.  The max and the row sum run on four / two
+      // independent accumulators (3-input FMNMX3), and every TMEM load is issued one chunk ahead of its use, so the
+      // 128-element dependent chains and the load latency of the round-1 kernel (profiles/r01_attn_fwd_ncu.txt) are gone.
       auto softmax_tile = [&](auto masked) {
         constexpr bool MASK = decltype(masked)::value;
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(tmem_s + lane_base + c * 32, v);
-          tmem_wait_ld();
+        float a0 = -INFINITY, a1 = -INFINITY, a2 = -INFINITY, a3 = -INFINITY;
+        uint32_t va[16], vb[16];
+        auto max16 = [&](const uint32_t (&v)[16], int c) {
 #pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            float sc = __uint_as_float(v[e]);
-            if (MASK && (k0 + c * 32 + e > qlim)) sc = -INFINITY;
-            mx = fmaxf(mx, sc);
+          for (int e = 0; e < 16; e += 8) {
+            float x[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+              x[t] = __uint_as_float(v[e + t]);
+              if (MASK && (k0 + c * 16 + e + t > qlim)) x[t] = -INFINITY;
+            }
+            a0 = fmax3(a0, x[0], x[1]);
+            a1 = fmax3(a1, x[2], x[3]);
+            a2 = fmax3(a2, x[4], x[5]);
+            a3 = fmax3(a3, x[6], x[7]);
           }
+        };
+        tmem_ld_32x32b_x16(tmem_s + lane_base, va);
+        tmem_wait_ld();
+#pragma unroll 1
+        for (int c = 0; c < 8; c += 2) {  // 16 columns per step, the next step's load in flight underneath
+          tmem_ld_32x32b_x16(tmem_s + lane_base + (c + 1) * 16, vb);
+          max16(va, c);
+          tmem_wait_ld();
+          tmem_ld_32x32b_x16(tmem_s + lane_base + ((c + 2) & 7) * 16, va);  // wraps to chunk 0 = pass 2's first load
+          max16(vb, c + 1);
+          tmem_wait_ld();
         }
+        mx = fmax3(m, fmaxf(a0, a1), fmaxf(a2, a3));
         const float m_use = (mx == -INFINITY) ? 0.f : mx;
         alpha = fast_exp2((m - m_use) * sl2);  // m = -inf -> 0
         const float mb = m_use * sl2;
@@ -210,25 +245,33 @@ attn_fwd_tc_kernel(const __grid_constant__ AttnTmaps tm, const AttnArgs a, const
           mbar_wait(o_full, (j - 1) & 1);
           tc_fence_after();
         }
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(tmem_s + lane_base + c * 32, v);
-          tmem_wait_ld();
-          uint32_t w[16];
+        float l0 = 0.f, l1 = 0.f;
+        auto exp16 = [&](const uint32_t (&v)[16], int c) {
+          uint32_t w[8];
 #pragma unroll
-          for (int e = 0; e < 32; e += 2) {
+          for (int e = 0; e < 16; e += 2) {
             float p0 = fast_exp2(fmaf(__uint_as_float(v[e]), sl2, -mb));
             float p1 = fast_exp2(fmaf(__uint_as_float(v[e + 1]), sl2, -mb));
             if (MASK) {
-              if (k0 + c * 32 + e > qlim) p0 = 0.f;
-              if (k0 + c * 32 + e + 1 > qlim) p1 = 0.f;
+              if (k0 + c * 16 + e > qlim) p0 = 0.f;
+              if (k0 + c * 16 + e + 1 > qlim) p1 = 0.f;
             }
-            lt += p0 + p1;
+            if (e & 2) l1 += p0 + p1;
+            else l0 += p0 + p1;
             w[e >> 1] = pack_bf16x2(p0, p1);
           }
-          store_tile_row_chunk(sP, r, c, w);
+          store_tile_row_16(sP, r, c, w);
+        };
+#pragma unroll 1
+        for (int c = 0; c < 8; c += 2) {
+          tmem_ld_32x32b_x16(tmem_s + lane_base + (c + 1) * 16, vb);
+          exp16(va, c);
+          tmem_wait_ld();
+          if (c + 2 < 8) tmem_ld_32x32b_x16(tmem_s + lane_base + (c + 2) * 16, va);
+          exp16(vb, c + 1);
+          tmem_wait_ld();
         }
+        lt = l0 + l1;
       };
       if (j == i) softmax_tile(std::true_type{});
       else softmax_tile(std::false_type{});

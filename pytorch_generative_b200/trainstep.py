@@ -14,6 +14,7 @@ import torch
 class GraphedTrainStep:
     def __init__(self, model, params, loss_fn, example_x, lr, lr_gamma, max_norm=1e50, warmup=3):
         self.model, self.params, self.loss_fn = model, list(params), loss_fn
+        self.lr0 = float(lr)
         self.lr = torch.tensor(float(lr), device=example_x.device)
         self.lr_gamma, self.max_norm = lr_gamma, max_norm
         self.opt = torch.optim.Adam(self.params, lr=self.lr, capturable=True)
@@ -37,6 +38,24 @@ class GraphedTrainStep:
         norm = torch.nn.utils.clip_grad_norm_(self.params, self.max_norm, foreach=True)
         self.opt.step()
         return loss.detach(), norm.detach()
+
+    @torch.no_grad()
+    def reset(self, state_dict=None, lr=None):
+        """Rewinds the step to a fresh optimizer (the capture's warm-up steps moved the weights and the Adam moments):
+        optionally reloads `state_dict` into the model, zeroes the moments / step counters in place (the graph keeps
+        reading the same tensors) and restores the learning rate."""
+        if state_dict is not None:
+            own = self.model.state_dict()
+            for k, v in state_dict.items():
+                if k in own:
+                    own[k].copy_(v)
+        for st in self.opt.state.values():
+            for t in st.values():
+                if torch.is_tensor(t):
+                    t.zero_()
+        if lr is not None:
+            self.lr0 = float(lr)
+        self.lr.fill_(self.lr0)
 
     def __call__(self, x):
         self.static_x.copy_(x, non_blocking=True)

@@ -389,6 +389,9 @@ ATTN_CASES = [
     (2, 1024, 1, 16, 128, True),
     (1, 64, 1, 16, 32, True),
     (3, 100, 2, 32, 32, False),
+    (6, 1024, 8, 64, 64, False),   # 384 work items: several per persistent CTA of the backward kernel
+    (10, 1024, 2, 16, 128, True),  # same for the 128-wide value slot (single K/V stage)
+    (40, 200, 4, 64, 64, True),    # 320 short items (two tiles), ragged
 ]
 
 
@@ -413,14 +416,14 @@ def _from_slots(t, H, d, slot):
     return t.reshape(t.shape[0], H, slot)[:, :, :d].reshape(t.shape[0], H * d)
 
 
-@pytest.mark.parametrize("impl", [1, 0])
+@pytest.mark.parametrize("impl", [1, 0, 3])
 @pytest.mark.parametrize("case", ATTN_CASES)
 def test_attention_fwd_bwd(L, case, impl):
     N, S, H, dk, dv, strict = case
     q, k, v, do = _attn_inputs(N, S, H, dk, dv)
     P = N * S
     o_ref, lse_ref, dq_ref, dk_ref, dv_ref = _attn_ref(q, k, v, do, N, S, H, dk, dv, strict)
-    if impl == 0:  # tensor-core kernels: 64-wide q/k slots, 64/128-wide v slots, scale from the true dk
+    if impl != 1:  # tensor-core kernels (0: product, 3: round-1 backward): 64-wide q/k slots, 64/128-wide v slots, scale from the true dk
         ks, vs = 64, (64 if dv <= 64 else 128)
         q, k, v, do = _to_slots(q, H, dk, ks), _to_slots(k, H, dk, ks), _to_slots(v, H, dv, vs), _to_slots(do, H, dv, vs)
     else:
@@ -445,33 +448,8 @@ def test_attention_fwd_bwd(L, case, impl):
     assert_close("attn dq", _from_slots(dq, H, dk, ks), dq_ref, rtol=2 ** -6, atol=2e-3)
     assert_close("attn dk", _from_slots(dk_, H, dk, ks), dk_ref, rtol=2 ** -6, atol=2e-3)
     assert_close("attn dv", _from_slots(dv_, H, dv, vs), dv_ref, rtol=2 ** -6, atol=2e-3)
-    if impl == 0 and dk < ks:
+    if impl != 1 and dk < ks:
         assert (dq.reshape(P, H, ks)[:, :, dk:] == 0).all() and (dk_.reshape(P, H, ks)[:, :, dk:] == 0).all()
-
-
-@pytest.mark.skipif(os.environ.get("PG_TEST_EXPERIMENTAL") != "1",
-                    reason="experimental split-phase attention backward (impl 2): opt-in, not the product path")
-@pytest.mark.parametrize("case", [c for c in ATTN_CASES if c[4] <= 64])
-def test_attention_bwd_split_experimental(L, case):
-    """impl = 2 of pg_causal_attn_bwd against the torch reference (forward through the product kernel)."""
-    N, S, H, dk, dv, strict = case
-    q, k, v, do = _attn_inputs(N, S, H, dk, dv)
-    P = N * S
-    o_ref, lse_ref, dq_ref, dk_ref, dv_ref = _attn_ref(q, k, v, do, N, S, H, dk, dv, strict)
-    q, k, v, do = _to_slots(q, H, dk, 64), _to_slots(k, H, dk, 64), _to_slots(v, H, dv, 64), _to_slots(do, H, dv, 64)
-    o = torch.empty(P, H * 64, device=_dev(), dtype=torch.bfloat16)
-    lse = torch.empty(N, H, S, device=_dev())
-    L.causal_attn_fwd(q, k, v, o, lse, N, S, H, 64, 64, strict, impl=0, dk_true=dk)
-    dq = torch.full((P, H * 64), float("nan"), device=_dev(), dtype=torch.bfloat16)
-    dk_ = torch.full((P, H * 64), float("nan"), device=_dev(), dtype=torch.bfloat16)
-    dv_ = torch.full((P, H * 64), float("nan"), device=_dev(), dtype=torch.bfloat16)
-    delta = torch.empty(N, H, S, device=_dev())
-    dq_acc = torch.zeros(P, H * 64, device=_dev())
-    L.causal_attn_bwd(q, k, v, o, do, lse, delta, dq_acc, dq, dk_, dv_, N, S, H, 64, 64, strict, impl=2, dk_true=dk)
-    torch.cuda.synchronize()
-    assert_close("attn dq", _from_slots(dq, H, dk, 64), dq_ref, rtol=2 ** -6, atol=2e-3)
-    assert_close("attn dk", _from_slots(dk_, H, dk, 64), dk_ref, rtol=2 ** -6, atol=2e-3)
-    assert_close("attn dv", _from_slots(dv_, H, dv, 64), dv_ref, rtol=2 ** -6, atol=2e-3)
 
 
 # --------------------------------------------------------------------------------------------------
