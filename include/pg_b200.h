@@ -84,6 +84,33 @@ typedef struct pg_gemm_epilogue {
 int pg_gemm_bf16(const void* A, int a_mn_major, int64_t lda, const void* B, int b_mn_major, int64_t ldb,
                  int M, int N, int K, int split_k, const pg_gemm_epilogue* epi, int impl, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Tap-loop convolution, im2col-free (CausalConv2d with wide channels — reference nn/convolution.py:41-43;
+ * GatedPixelCNN 1xN / Nx1 stacks — gated_pixel_cnn.py:63-99 with the crops at 115,121; PixelSNAIL 2x2 —
+ * pixel_snail.py:41-56), forward and both gradients on the pg_gemm_bf16 kernel:
+ *   conv(x)[p] = sum_t W_t . x[p + (dy_t, dx_t)], zero outside the image (the reference's pad + front crop).
+ * The shifted operand is never materialised: for every tap the TMA unit loads the [C, W, H, N] box displaced by
+ * (dy_t, dx_t) from the pixel-major tensor (out-of-image elements arrive as zeros) and the tensor core accumulates
+ * one K slab per (tap, 64 channels).  Epilogue semantics are pg_gemm_bf16's.
+ *   PG_CONV_FWD:   A = x  [P, >=C] bf16, C = Cin;  B = packed weight [Cout, T*Cin] (tap-major columns);
+ *                  M = P, N = Cout, K = T*Cin.
+ *   PG_CONV_DGRAD: A = dy [P, >=C] bf16, C = Cout, taps negated by the caller;  B = the same packed weight;
+ *                  M = P, N = Cin (= the per-tap column stride of the packed weight), K = T*Cout.
+ *   PG_CONV_WGRAD: A = dy [P, Cout] bf16;  B = x [P, >=C] bf16, C = Cin;  M = Cout, N = T*Cin, K = P;
+ *                  out_f32 [Cout, T*Cin] accumulated (split_k as pg_gemm_bf16).
+ * Geometry limits (else use pg_tap_gather): C % 64 == 0, W | 64, H*W % 128 == 0, <= 32 taps, |offset| <= 64.
+ * ------------------------------------------------------------------------------------------- */
+enum { PG_CONV_FWD = 1, PG_CONV_DGRAD = 2, PG_CONV_WGRAD = 3 };
+typedef struct pg_conv_geom {
+  int32_t mode;        /* PG_CONV_* */
+  int32_t N, H, W;     /* images, rows, columns: P = N*H*W pixels */
+  int32_t C;           /* channels of the shifted tensor (per-tap K extent for fwd / dgrad, per-tap N extent for wgrad) */
+  int32_t n_taps;
+  int32_t dy[32], dx[32];
+} pg_conv_geom;
+int pg_gemm_bf16_conv(const void* A, int64_t lda, const void* B, int64_t ldb, int M, int N, int K, int split_k,
+                      const pg_gemm_epilogue* epi, const pg_conv_geom* geom, void* stream);
+
 /* Column sums of a bf16 [P, C] matrix into fp32 out[C] (bias gradients; accumulate=1 adds). */
 int pg_colsum_bf16(const void* x, int64_t ld, int P, int C, float* out, int accumulate, void* stream);
 int pg_colsum_f32(const float* x, int64_t ld, int P, int C, float* out, int accumulate, void* stream);

@@ -8,6 +8,7 @@ are not CUDA tensors, the call raises.
 """
 
 import ctypes
+import functools
 import math
 import os
 
@@ -36,9 +37,19 @@ class GemmEpilogue(ctypes.Structure):
     ]
 
 
+class ConvGeom(ctypes.Structure):
+    """Mirror of `pg_conv_geom` (include/pg_b200.h)."""
+
+    _fields_ = [("mode", ctypes.c_int32), ("N", ctypes.c_int32), ("H", ctypes.c_int32), ("W", ctypes.c_int32),
+                ("C", ctypes.c_int32), ("n_taps", ctypes.c_int32), ("dy", ctypes.c_int32 * 32), ("dx", ctypes.c_int32 * 32)]
+
+
+CONV_FWD, CONV_DGRAD, CONV_WGRAD = 1, 2, 3
+
 # name -> argtypes (restype is always int unless listed in _SPECIAL)
 _SIGNATURES = {
     "pg_gemm_bf16": [_vp, _i32, _i64, _vp, _i32, _i64, _i32, _i32, _i32, _i32, ctypes.POINTER(GemmEpilogue), _i32, _vp],
+    "pg_gemm_bf16_conv": [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, ctypes.POINTER(GemmEpilogue), ctypes.POINTER(ConvGeom), _vp],
     "pg_colsum_bf16": [_vp, _i64, _i32, _i32, _vp, _i32, _vp],
     "pg_colsum_f32": [_vp, _i64, _i32, _i32, _vp, _i32, _vp],
     "pg_layernorm_fwd": [_vp, _vp, _vp, _i32, _i32, _f32, _vp, _vp, _vp, _vp, _vp],
@@ -111,6 +122,28 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+def _device_guarded(fn):
+    """Runs a binding on the device its tensors live on: every operand must share one CUDA device; when that is not
+    the current device the call (stream lookup, TMA descriptor encode, launch) happens under `torch.cuda.device(idx)`,
+    like torch's own ops do."""
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        idx = None
+        for a in (*args, *kwargs.values()):
+            if torch.is_tensor(a) and a.is_cuda:
+                if idx is None:
+                    idx = a.device.index
+                elif a.device.index != idx:
+                    raise RuntimeError(f"{fn.__name__}: operands live on different CUDA devices ({idx} and {a.device.index})")
+        if idx is None or idx == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(idx):
+            return fn(*args, **kwargs)
+
+    return wrapper
+
+
 def _pm(t):
     """Checks a pixel-major 2-D view (unit inner stride) and returns (ptr, pitch)."""
     assert t.dim() == 2 and t.stride(1) == 1, f"expected a [P, C] matrix with unit inner stride, got {t.shape} {t.stride()}"
@@ -139,6 +172,7 @@ def sm_count():
 # ------------------------------------------------------------------------------------------------
 # GEMM
 # ------------------------------------------------------------------------------------------------
+@_device_guarded
 def gemm(A, B, M, N, K, *, a_mn=False, b_mn=False, bias=None, aux=None, dact=ACT_NONE, res0=None, res1=None,
          out_bf16=None, out_pre=None, out_f32=None, act=ACT_NONE, accumulate=False, alpha=1.0, split_k=1, impl=0):
     """acc = A·Bᵀ (see pg_gemm_bf16 in include/pg_b200.h); all tensors are 2-D bf16/fp32 CUDA views."""
@@ -146,6 +180,61 @@ def gemm(A, B, M, N, K, *, a_mn=False, b_mn=False, bias=None, aux=None, dact=ACT
     assert A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16
     a_ptr, lda = _pm(A)
     b_ptr, ldb = _pm(B)
+    e = _epilogue(M, N, bias, aux, dact, res0, res1, out_bf16, out_pre, out_f32, act, accumulate, alpha)
+    hook = gemm_timing_hook
+    if hook is not None:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+    _check(lib.pg_gemm_bf16(a_ptr, int(a_mn), lda, b_ptr, int(b_mn), ldb, M, N, K, split_k, ctypes.byref(e), impl,
+                            _stream()), "pg_gemm_bf16")
+    if hook is not None:
+        ev1.record()
+        hook(2.0 * M * N * K, ev0, ev1, _gemm_io(M, N, K, out_bf16, out_pre, out_f32, aux, res0, res1))
+
+
+def _gemm_io(M, N, K, out_bf16, out_pre, out_f32, aux, res0, res1):
+    """Algorithmic HBM bytes of one contraction: both operands once, every epilogue tensor once."""
+    return 2 * (M * K + N * K) + M * N * (2 * (out_bf16 is not None) + 2 * (out_pre is not None) + 4 * (out_f32 is not None)
+                                          + 2 * (aux is not None) + 4 * (res0 is not None) + 4 * (res1 is not None))
+
+
+@_device_guarded
+def gemm_conv(A, B, M, N, K, mode, n_img, H, W, C, taps, *, bias=None, aux=None, dact=ACT_NONE, res0=None, res1=None,
+              out_bf16=None, out_pre=None, out_f32=None, act=ACT_NONE, accumulate=False, alpha=1.0, split_k=1):
+    """Tap-loop convolution on the GEMM kernel (pg_gemm_bf16_conv); `taps` = [(dy, dx), ...] as the kernel applies them
+    (the caller negates them for dgrad)."""
+    lib = load()
+    assert A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16
+    a_ptr, lda = _pm(A)
+    b_ptr, ldb = _pm(B)
+    e = _epilogue(M, N, bias, aux, dact, res0, res1, out_bf16, out_pre, out_f32, act, accumulate, alpha)
+    g = ConvGeom()
+    g.mode, g.N, g.H, g.W, g.C, g.n_taps = mode, n_img, H, W, C, len(taps)
+    for t, (dy, dx) in enumerate(taps):
+        g.dy[t], g.dx[t] = int(dy), int(dx)
+    hook = gemm_timing_hook
+    if hook is not None:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+    _check(lib.pg_gemm_bf16_conv(a_ptr, lda, b_ptr, ldb, M, N, K, split_k, ctypes.byref(e), ctypes.byref(g), _stream()),
+           "pg_gemm_bf16_conv")
+    if hook is not None:
+        ev1.record()
+        # the shifted operand is read once per tap from L2 but only once from HBM
+        io = _gemm_io(M, N, K, out_bf16, out_pre, out_f32, aux, res0, res1)
+        if mode == CONV_WGRAD:
+            io -= 2 * K * (N - C)
+        else:
+            io -= 2 * M * (K - C)
+        hook(2.0 * M * N * K, ev0, ev1, io)
+
+
+def conv_gemm_supported(H, W, C):
+    """Geometry the TMA tap loop handles (pg_gemm_bf16_conv); other shapes go through pg_tap_gather."""
+    return C % 64 == 0 and 1 <= W <= 64 and 64 % W == 0 and (H * W) % 128 == 0
+
+
+def _epilogue(M, N, bias, aux, dact, res0, res1, out_bf16, out_pre, out_f32, act, accumulate, alpha):
     e = GemmEpilogue()
     e.bias = _ptr(bias)
     if bias is not None:
@@ -171,19 +260,10 @@ def gemm(A, B, M, N, K, *, a_mn=False, b_mn=False, bias=None, aux=None, dact=ACT
         assert out_f32.dtype == torch.float32 and out_f32.shape[0] >= M
         e.out_f32, e.ld_out_f32 = _pm(out_f32)
     e.act, e.dact, e.accumulate, e.alpha = act, dact, int(accumulate), alpha
-    hook = gemm_timing_hook
-    if hook is not None:
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record()
-    _check(lib.pg_gemm_bf16(a_ptr, int(a_mn), lda, b_ptr, int(b_mn), ldb, M, N, K, split_k, ctypes.byref(e), impl,
-                            _stream()), "pg_gemm_bf16")
-    if hook is not None:
-        ev1.record()
-        io = 2 * (M * K + N * K) + M * N * (2 * (out_bf16 is not None) + 2 * (out_pre is not None) + 4 * (out_f32 is not None)
-                                            + 2 * (aux is not None) + 4 * (res0 is not None) + 4 * (res1 is not None))
-        hook(2.0 * M * N * K, ev0, ev1, io)
+    return e
 
 
+@_device_guarded
 def colsum(x, out, accumulate=False):
     lib = load()
     p, ld = _pm(x)
@@ -196,6 +276,7 @@ def colsum(x, out, accumulate=False):
 # ------------------------------------------------------------------------------------------------
 # LayerNorm / gated activation / loss / converters
 # ------------------------------------------------------------------------------------------------
+@_device_guarded
 def layernorm_fwd(x, gamma, beta, eps, y_bf16=None, y_f32=None, mean=None, rstd=None):
     lib = load()
     P, C = x.shape
@@ -204,6 +285,7 @@ def layernorm_fwd(x, gamma, beta, eps, y_bf16=None, y_f32=None, mean=None, rstd=
                                 _ptr(rstd), _stream()), "pg_layernorm_fwd")
 
 
+@_device_guarded
 def layernorm_bwd(dy, x, gamma, mean, rstd, dres0=None, dres1=None, dx_f32=None, dx_bf16=None, dgamma=None,
                   dbeta=None, dx_colsum=None):
     lib = load()
@@ -217,6 +299,7 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, dres0=None, dres1=None, dx_f32=None,
            "pg_layernorm_bwd")
 
 
+@_device_guarded
 def gated_act_fwd(x, y, act):
     lib = load()
     P, C2 = x.shape
@@ -225,6 +308,7 @@ def gated_act_fwd(x, y, act):
                                 int(y.dtype == torch.float32), _stream()), "pg_gated_act_fwd")
 
 
+@_device_guarded
 def gated_act_bwd(x, dy, dx, act):
     lib = load()
     P, C2 = x.shape
@@ -233,6 +317,7 @@ def gated_act_bwd(x, dy, dx, act):
                                 C2 // 2, act, _ptr(dx), int(dx.dtype == torch.float32), _stream()), "pg_gated_act_bwd")
 
 
+@_device_guarded
 def bce_logits(logits, target, grad_scale, loss_sum, dlogits=None):
     lib = load()
     assert logits.dtype == torch.float32 and target.dtype == torch.float32
@@ -241,6 +326,7 @@ def bce_logits(logits, target, grad_scale, loss_sum, dlogits=None):
                                      _ptr(dlogits), _stream()), "pg_bce_logits_fwd_bwd")
 
 
+@_device_guarded
 def nchw_to_pm(x, out):
     """x: [N, C, H, W] fp32 contiguous -> out: [N*H*W, >=C] bf16/fp32 (pixel-major)."""
     lib = load()
@@ -250,6 +336,7 @@ def nchw_to_pm(x, out):
     _check(lib.pg_nchw_to_pm(_ptr(x), N, C, H * W, p, int(out.dtype == torch.float32), ld, _stream()), "pg_nchw_to_pm")
 
 
+@_device_guarded
 def pm_to_nchw(x_pm, out, act=ACT_NONE):
     lib = load()
     N, C, H, W = out.shape
@@ -259,6 +346,7 @@ def pm_to_nchw(x_pm, out, act=ACT_NONE):
            "pg_pm_to_nchw")
 
 
+@_device_guarded
 def dact_mul(dy, pre, act, out):
     """out = bf16(dy * act'(pre)); dy/out bf16 [P, C] views, pre fp32."""
     lib = load()
@@ -268,6 +356,7 @@ def dact_mul(dy, pre, act, out):
     _check(lib.pg_dact_mul(dp, ldd, pp, ldp, P, C, act, op, ldo, _stream()), "pg_dact_mul")
 
 
+@_device_guarded
 def cast_bf16(x, y):
     lib = load()
     assert x.dtype == torch.float32 and y.dtype == torch.bfloat16 and x.is_contiguous() and y.is_contiguous()
@@ -277,6 +366,7 @@ def cast_bf16(x, y):
 # ------------------------------------------------------------------------------------------------
 # Attention / small conv
 # ------------------------------------------------------------------------------------------------
+@_device_guarded
 def causal_attn_fwd(q, k, v, o, lse, N, S, H, dk, dv, strict, impl=0, dk_true=None):
     """dk is the column width of a head slot; dk_true (default dk) sets the 1/sqrt(dk) scale."""
     lib = load()
@@ -286,6 +376,7 @@ def causal_attn_fwd(q, k, v, o, lse, N, S, H, dk, dv, strict, impl=0, dk_true=No
                                   impl, _stream()), "pg_causal_attn_fwd")
 
 
+@_device_guarded
 def causal_attn_bwd(q, k, v, o, do, lse, delta, dq_accum, dq, dk_, dv_, N, S, H, dk, dv, strict, impl=0, dk_true=None):
     lib = load()
     (qp, ldq), (kp, ldk), (vp, ldv), (op, ldo), (dop, lddo) = _pm(q), _pm(k), _pm(v), _pm(o), _pm(do)
@@ -296,6 +387,7 @@ def causal_attn_bwd(q, k, v, o, do, lse, delta, dq_accum, dq, dk_, dv_, N, S, H,
                                   impl, _stream()), "pg_causal_attn_bwd")
 
 
+@_device_guarded
 def conv_small_fwd(x, w, bias, pad, out_f32=None, out_bf16=None, act_bf16=ACT_NONE, pre_act=ACT_NONE):
     lib = load()
     N, Cin, H, W = x.shape
@@ -305,6 +397,7 @@ def conv_small_fwd(x, w, bias, pad, out_f32=None, out_bf16=None, act_bf16=ACT_NO
                                  _ptr(out_f32), _ptr(out_bf16), act_bf16, _stream()), "pg_conv_small_fwd")
 
 
+@_device_guarded
 def conv_small_bwd(x, w, dy_pm, pad, dw=None, dbias=None, dx=None, pre_act=ACT_NONE):
     lib = load()
     N, Cin, H, W = x.shape
@@ -319,6 +412,7 @@ def _int_array(vals):
     return arr
 
 
+@_device_guarded
 def tap_gather(x_pm, N, H, W, C, taps, act, out):
     """x_pm: [P, >=C] bf16; taps: list of (dy, dx); out: [P, T*C] bf16 contiguous."""
     lib = load()
@@ -329,6 +423,7 @@ def tap_gather(x_pm, N, H, W, C, taps, act, out):
                              act, _ptr(out), _stream()), "pg_tap_gather")
 
 
+@_device_guarded
 def tap_scatter(dxcat, N, H, W, C, taps, act, x_pre, dx_f32=None, dx_bf16=None):
     lib = load()
     assert dxcat.is_contiguous() and dxcat.dtype == torch.bfloat16
@@ -343,6 +438,7 @@ def tap_scatter(dxcat, N, H, W, C, taps, act, x_pre, dx_f32=None, dx_bf16=None):
                               _stream()), "pg_tap_scatter")
 
 
+@_device_guarded
 def attn_decode(q, k_new, v_new, k_cache, v_cache, o, pos_dev, N, S, H, dk, dv, strict, dk_true=None):
     """One new position per image against the KV caches (see pg_attn_decode); pos_dev: int32 device scalar."""
     lib = load()

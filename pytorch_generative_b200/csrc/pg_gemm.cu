@@ -34,7 +34,19 @@ struct EpiMaps {
   CUtensorMap res0, res1, aux, out_f32, out_bf16, out_pre;
 };
 
+// Tap-loop convolution (pg_gemm_bf16_conv): the shifted operand is read straight from the pixel-major activation
+// tensor through a 4-D TMA map [C, W, H, N]; out-of-image coordinates are zero-filled by the TMA unit, which is the
+// reference's zero padding.  mode 1: A is shifted (forward / dgrad, K = taps x channel slabs); mode 2: B is shifted
+// (wgrad, the taps are extra N blocks).
+struct ConvGeom {
+  int mode, H, W, C, T;
+  int cslabs;  // C / 64 (mode 1): K iterations per tap
+  int nbpt;    // mode 2: N blocks per tap (C / BN)
+  int8_t dy[32], dx[32];
+};
+
 struct GemmParams {
+  ConvGeom conv;
   int M, N, K;
   int num_m_blk, num_n_blk;
   int k_iters;      // ceil(K / BK)
@@ -289,18 +301,53 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // both CTAs load their halves; all bytes are accounted on the leader's barrier
             if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * STAGE_BYTES);
             const int row0 = m_blk * MT + rank * BM, nb0 = n_blk * BN + rank * B_ROWS;
-            tma_load_2d_2sm(sA, &tmA, &full_bar[s], kit * BK, row0);
+            int bcol = nb0, brow = kit * BK;  // MN-major B coordinates
+            if (p.conv.mode == 1) {
+              const int t = kit / p.conv.cslabs, cs = kit - t * p.conv.cslabs;
+              const int hw = p.conv.H * p.conv.W, n = row0 / hw, h0 = (row0 - n * hw) / p.conv.W;
+              tma_load_4d_2sm(sA, &tmA, &full_bar[s], cs * 64, p.conv.dx[t], h0 + p.conv.dy[t], n);
+              bcol = t * p.N + nb0;  // dgrad: W^T of tap t starts at column t * Cin of the packed weight
+              brow = cs * 64;
+            } else {
+              tma_load_2d_2sm(sA, &tmA, &full_bar[s], kit * BK, row0);
+            }
             if (!B_MN) {
               tma_load_2d_2sm(sB, &tmB, &full_bar[s], kit * BK, nb0);
             } else {
 #pragma unroll
               for (int j = 0; j < B_ROWS / 64; ++j)
-                tma_load_2d_2sm(sB + j * (BK * 128), &tmB, &full_bar[s], nb0 + j * 64, kit * BK);
+                tma_load_2d_2sm(sB + j * (BK * 128), &tmB, &full_bar[s], bcol + j * 64, brow);
             }
             if (++s == STAGES) { s = 0; ph ^= 1; }
             continue;
           }
           mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+          if (p.conv.mode != 0) {
+            const int hw = p.conv.H * p.conv.W;
+            if (p.conv.mode == 1) {  // A = activations under tap t (forward / dgrad)
+              const int t = kit / p.conv.cslabs, cs = kit - t * p.conv.cslabs;
+              const int row0 = m_blk * BM, n = row0 / hw, h0 = (row0 - n * hw) / p.conv.W;
+              tma_load_4d(sA, &tmA, &full_bar[s], cs * 64, p.conv.dx[t], h0 + p.conv.dy[t], n);
+              if (!B_MN) {
+                tma_load_2d(sB, &tmB, &full_bar[s], kit * BK, n_blk * BN);
+              } else {
+#pragma unroll
+                for (int j = 0; j < BN / 64; ++j)
+                  tma_load_2d(sB + j * (BK * 128), &tmB, &full_bar[s], t * p.N + n_blk * BN + j * 64, cs * 64);
+              }
+            } else {  // wgrad: A = dY (MN-major), B = activations under the tap this N block belongs to
+              const int t = n_blk / p.conv.nbpt, nb = n_blk - t * p.conv.nbpt;
+              const int pix0 = kit * BK, n = pix0 / hw, h0 = (pix0 - n * hw) / p.conv.W;
+#pragma unroll
+              for (int j = 0; j < BM / 64; ++j)
+                tma_load_2d(sA + j * (BK * 128), &tmA, &full_bar[s], m_blk * BM + j * 64, kit * BK);
+#pragma unroll
+              for (int j = 0; j < BN / 64; ++j)
+                tma_load_4d(sB + j * (BK * 128), &tmB, &full_bar[s], nb * BN + j * 64, p.conv.dx[t], h0 + p.conv.dy[t], n);
+            }
+            if (++s == STAGES) { s = 0; ph ^= 1; }
+            continue;
+          }
           if (!A_MN) {
             tma_load_2d(sA, &tmA, &full_bar[s], kit * BK, m_blk * BM);  // box {64 k, 128 rows}
           } else {
@@ -633,13 +680,29 @@ int launch_tc(const void* A, int64_t lda, const void* B, int64_t ldb, GemmParams
   constexpr int B_ROWS = TWO ? BN / 2 : BN;
   if (TWO) p.num_m_blk = (p.M + 2 * BM - 1) / (2 * BM);
   CUtensorMap tmA, tmB;
-  if (!A_MN) {
+  const ConvGeom& cg = p.conv;
+  auto conv_map = [&](CUtensorMap* out, const void* base, int64_t ld, int pixels_per_box) {
+    const int64_t n_img = (cg.mode == 1 ? (int64_t)p.M : (int64_t)p.K) / ((int64_t)cg.H * cg.W);
+    uint64_t dims[4] = {(uint64_t)cg.C, (uint64_t)cg.W, (uint64_t)cg.H, (uint64_t)n_img};
+    uint64_t strides[3] = {(uint64_t)ld * 2, (uint64_t)cg.W * ld * 2, (uint64_t)cg.H * cg.W * ld * 2};
+    uint32_t box[4] = {64, (uint32_t)cg.W, (uint32_t)(pixels_per_box / cg.W), 1};
+    return pg_make_tmap_nd_bf16(out, base, 4, dims, strides, box, 1);
+  };
+  if (cg.mode == 1) {
+    if (conv_map(&tmA, A, lda, BM)) return 1;
+  } else if (!A_MN) {
     if (pg_make_tmap_2d_bf16(&tmA, A, p.M, p.K, lda, BM, BK)) return 1;
   } else {
     if (pg_make_tmap_2d_bf16(&tmA, A, p.K, p.M, lda, BK, 64)) return 1;
   }
-  if (!B_MN) {
+  if (cg.mode == 2) {
+    PG_REQUIRE(B_MN && cg.C % BN == 0, "pg_gemm_bf16_conv(wgrad): channels (%d) must be a multiple of the N tile (%d)", cg.C, BN);
+    p.conv.nbpt = cg.C / BN;
+    if (conv_map(&tmB, B, ldb, BK)) return 1;
+  } else if (!B_MN) {
     if (pg_make_tmap_2d_bf16(&tmB, B, p.N, p.K, ldb, B_ROWS, BK)) return 1;
+  } else if (cg.mode == 1) {  // dgrad: the packed weight [Cout, T * Cin] read K-rows x N-columns, tap t at column t * Cin
+    if (pg_make_tmap_2d_bf16(&tmB, B, cg.C, (uint64_t)cg.T * p.N, ldb, BK, 64)) return 1;
   } else {
     if (pg_make_tmap_2d_bf16(&tmB, B, p.K, p.N, ldb, BK, 64)) return 1;
   }
@@ -719,6 +782,7 @@ int dispatch_bn(const void* A, int64_t lda, const void* B, int64_t ldb, GemmPara
   else if (p.N > 32) bn = 64;
   else bn = 32;
   if (B_MN && bn < 64) bn = 64;  // MN-major operands are staged in 64-wide swizzle atoms
+  if (p.conv.mode == 2) bn = (p.conv.C % 256 == 0) ? 256 : (p.conv.C % 128 == 0) ? 128 : 64;  // taps are whole N blocks
   const pg_gemm_epilogue& e = p.epi;
   const int epi = (e.res0 ? SLAB_F32 : 0) + (e.res1 ? SLAB_F32 : 0) + (e.dact != PG_ACT_NONE ? SLAB_BF16 : 0) +
                   (e.out_f32 ? SLAB_F32 : 0) + (e.out_pre ? SLAB_BF16 : 0) + (e.out_bf16 ? SLAB_BF16 : 0);
@@ -744,9 +808,9 @@ int dispatch_bn(const void* A, int64_t lda, const void* B, int64_t ldb, GemmPara
   if (bn == 256) {
     // fp32-heavy staged epilogues (residual stream in/out) need more slab space than a 256-wide tile leaves
     // next to a >= 3-deep operand pipeline; those GEMMs are HBM-bound anyway, so take the 128-wide tile.
-    if (staged && (SMEM_LIMIT - 2 * epi - 1536) / (A_STAGE_BYTES + 256 * BK * 2) < 3) bn = 128;
+    if (staged && (SMEM_LIMIT - 2 * epi - 1536) / (A_STAGE_BYTES + 256 * BK * 2) < 3 && (p.conv.mode != 2 || p.conv.C % 128 == 0)) bn = 128;
     // Narrow problems with few tiles prefer 128 to spread over more SMs.
-    if (bn == 256 && ((p.M + BM - 1) / BM) * ((p.N + 255) / 256) * p.splits < pg_num_sms() && p.N % 256 != 0) bn = 128;
+    if (bn == 256 && p.conv.mode != 2 && ((p.M + BM - 1) / BM) * ((p.N + 255) / 256) * p.splits < pg_num_sms() && p.N % 256 != 0) bn = 128;
   }
   p.num_n_blk = (p.N + bn - 1) / bn;
   switch (bn) {
@@ -759,8 +823,8 @@ int dispatch_bn(const void* A, int64_t lda, const void* B, int64_t ldb, GemmPara
 
 }  // namespace
 
-extern "C" int pg_gemm_bf16(const void* A, int a_mn_major, int64_t lda, const void* B, int b_mn_major, int64_t ldb,
-                            int M, int N, int K, int split_k, const pg_gemm_epilogue* epi, int impl, void* stream_) {
+static int gemm_entry(const void* A, int a_mn_major, int64_t lda, const void* B, int b_mn_major, int64_t ldb, int M, int N,
+                      int K, int split_k, const pg_gemm_epilogue* epi, int impl, const ConvGeom* conv, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   PG_REQUIRE(A && B && epi, "pg_gemm_bf16: null operand");
   PG_REQUIRE(M > 0 && N > 0 && K > 0, "pg_gemm_bf16: empty problem M=%d N=%d K=%d", M, N, K);
@@ -774,6 +838,7 @@ extern "C" int pg_gemm_bf16(const void* A, int a_mn_major, int64_t lda, const vo
                "pg_gemm_bf16: split_k > 1 requires accumulate=1 into out_f32 only");
   GemmParams p;
   memset(&p, 0, sizeof(p));
+  if (conv) p.conv = *conv;
   p.M = M; p.N = N; p.K = K;
   p.num_m_blk = (M + BM - 1) / BM;
   p.num_n_blk = 0;
@@ -823,4 +888,41 @@ extern "C" int pg_gemm_bf16(const void* A, int a_mn_major, int64_t lda, const vo
   if (!a_mn_major && b_mn_major) return dispatch_bn<false, true>(A, lda, B, ldb, p, stream);
   if (a_mn_major && b_mn_major) return dispatch_bn<true, true>(A, lda, B, ldb, p, stream);
   return dispatch_bn<true, false>(A, lda, B, ldb, p, stream);
+}
+
+extern "C" int pg_gemm_bf16(const void* A, int a_mn_major, int64_t lda, const void* B, int b_mn_major, int64_t ldb,
+                            int M, int N, int K, int split_k, const pg_gemm_epilogue* epi, int impl, void* stream_) {
+  return gemm_entry(A, a_mn_major, lda, B, b_mn_major, ldb, M, N, K, split_k, epi, impl, nullptr, stream_);
+}
+
+// Tap-loop convolution on the same kernel (see ConvGeom): forward / dgrad read the activation (or output-gradient)
+// tensor under each tap's shift, wgrad reads the shifted activations as its B operand.
+extern "C" int pg_gemm_bf16_conv(const void* A, int64_t lda, const void* B, int64_t ldb, int M, int N, int K, int split_k,
+                                 const pg_gemm_epilogue* epi, const pg_conv_geom* g, void* stream_) {
+  PG_REQUIRE(g, "pg_gemm_bf16_conv: null geometry");
+  PG_REQUIRE(g->mode >= PG_CONV_FWD && g->mode <= PG_CONV_WGRAD, "pg_gemm_bf16_conv: mode %d", g->mode);
+  PG_REQUIRE(g->n_taps >= 1 && g->n_taps <= 32, "pg_gemm_bf16_conv: 1..32 taps (got %d)", g->n_taps);
+  PG_REQUIRE(g->C % 64 == 0 && g->W >= 1 && g->W <= 64 && 64 % g->W == 0 && ((int64_t)g->H * g->W) % 128 == 0,
+             "pg_gemm_bf16_conv: needs C %% 64 == 0, W | 64 and H*W %% 128 == 0 (C=%d H=%d W=%d); use pg_tap_gather otherwise",
+             g->C, g->H, g->W);
+  const int64_t P = (int64_t)g->N * g->H * g->W;
+  ConvGeom cg;
+  memset(&cg, 0, sizeof(cg));
+  cg.H = g->H; cg.W = g->W; cg.C = g->C; cg.T = g->n_taps;
+  cg.cslabs = g->C / 64;
+  for (int t = 0; t < g->n_taps; ++t) {
+    PG_REQUIRE(g->dy[t] >= -64 && g->dy[t] <= 64 && g->dx[t] >= -64 && g->dx[t] <= 64, "pg_gemm_bf16_conv: tap offset out of range");
+    cg.dy[t] = (int8_t)g->dy[t];
+    cg.dx[t] = (int8_t)g->dx[t];
+  }
+  if (g->mode == PG_CONV_WGRAD) {
+    // dW[cout, t*C + c] += sum_p dY[p, cout] * X[p + off_t, c]:  A = dY (MN-major), B = X (shifted), K = pixels
+    PG_REQUIRE(K == P && N == g->n_taps * g->C, "pg_gemm_bf16_conv(wgrad): K must be N*H*W and N = taps * C");
+    cg.mode = 2;
+    return gemm_entry(A, 1, lda, B, 1, ldb, M, N, K, split_k, epi, 0, &cg, stream_);
+  }
+  // forward: A = X (shifted), B = W [Cout, T*C] K-major.  dgrad: A = dY (shifted by -off), B = W [C, T*N] read MN-major.
+  PG_REQUIRE(M == P && K == g->n_taps * g->C, "pg_gemm_bf16_conv: M must be N*H*W and K = taps * C");
+  cg.mode = 1;
+  return gemm_entry(A, 0, lda, B, g->mode == PG_CONV_DGRAD ? 1 : 0, ldb, M, N, K, split_k, epi, 0, &cg, stream_);
 }
