@@ -35,7 +35,10 @@ unsigned long long pg_launch_count(void);
 /* Activation ids (shared by the GEMM epilogue and the elementwise kernels). */
 enum { PG_ACT_NONE = 0, PG_ACT_RELU = 1, PG_ACT_GELU = 2, PG_ACT_ELU = 3, PG_ACT_TANH = 4,
        /* pg_gemm_epilogue.dact only: `aux` already holds the derivative (see PG_ACT_STORE_DERIV) */
-       PG_ACT_GIVEN = 5 };
+       PG_ACT_GIVEN = 5,
+       /* pg_gemm_epilogue.dact only: `aux` holds the ACTIVATED value (relu(pre) / elu(pre)), from which the derivative
+        * follows without the pre-activation: relu' = [a > 0], elu' = a > 0 ? 1 : a + 1 */
+       PG_ACT_RELU_OUT = 6, PG_ACT_ELU_OUT = 7 };
 /* OR-ed into pg_gemm_epilogue.act: out_pre receives act'(pre) instead of pre, so that the matching dgrad epilogue
  * (dact = PG_ACT_GIVEN) is a single multiply. */
 #define PG_ACT_STORE_DERIV 0x100
@@ -160,6 +163,11 @@ int pg_pm_to_nchw(const void* x_pm, int x_is_f32, int64_t ld_x, int N, int C, in
 /* out = bf16(dy * act'(pre)): gradient through such an output activation. */
 int pg_dact_mul(const void* dy_bf16, int64_t ld_dy, const float* pre_f32, int64_t ld_pre, int P, int C, int act,
                 void* out_bf16, int64_t ld_out, void* stream);
+/* out = bf16(act(x)) over a pitched pixel-major [P, C] matrix (fp32 or bf16 in): builds the tensor-core operand of a
+ * convolution whose input activation (ReLU / ELU in front of the conv: pixel_cnn.py:35-49, pixel_snail.py:27-28) was not
+ * already emitted by the producing GEMM's epilogue.  C % 8 == 0. */
+int pg_act_cast_bf16(const void* x, int x_is_f32, int64_t ld_x, int P, int C, int act, void* out_bf16, int64_t ld_out,
+                     void* stream);
 /* fp32 -> bf16 cast of a dense buffer (weights packing; masked taps already zeroed by the caller). */
 int pg_cast_f32_to_bf16(const float* x, void* y, int64_t numel, void* stream);
 
@@ -222,6 +230,26 @@ int pg_tap_gather(const void* x_pm, int64_t ld_x, int N, int H, int W, int C, in
 int pg_tap_scatter(const void* dxcat /* bf16 [P, T*C] */, int N, int H, int W, int C, int T, const int* dy,
                    const int* dx, int act, const void* x_pre /* bf16 [P, ld_pre] or NULL */, int64_t ld_pre,
                    float* dx_f32, void* dx_bf16, int64_t ld_dx, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Optimizer part of the training step — reference trainer.py:182-191 (`clip_grad_norm_(model.parameters(), max_norm)`
+ * then `optimizer.step()` with torch.optim.Adam as every recipe builds it, e.g. image_gpt.py:155) over ALL parameters in
+ * two launches.  Tensors are given as device arrays of device pointers (one entry per parameter, fp32, contiguous);
+ * `numel` [n_tensors] int64 (device); `chunks` [n_chunks] pairs of int32 (tensor index, chunk index) (device): block b
+ * handles elements [chunk * chunk_elems, +chunk_elems) of its tensor.
+ *   pg_grad_sqnorm: partials[b] = sum of g^2 over block b's chunk.
+ *   pg_adam_step:   norm = sqrt(sum partials) (same order in every block: deterministic); norm_out[0] = norm;
+ *                   if skip_above > 0 and norm > skip_above: nothing is updated and norm_out[1] = 0 (the trainer's
+ *                   skip_grad_norm rule), else norm_out[1] = 1 and, with c = min(1, max_norm / (norm + 1e-6)):
+ *                   g *= c (written back only when c < 1), m = b1 m + (1-b1) g, v = b2 v + (1-b2) g^2,
+ *                   p -= lr / (1-b1^step) * m / (sqrt(v) / sqrt(1-b2^step) + eps)      (torch.optim.Adam, no amsgrad).
+ * ------------------------------------------------------------------------------------------- */
+int pg_grad_sqnorm(const void* grad_ptrs, const int64_t* numel, const void* chunks, int n_chunks, int chunk_elems,
+                   float* partials, void* stream);
+int pg_adam_step(const void* param_ptrs, const void* grad_ptrs, const void* exp_avg_ptrs, const void* exp_avg_sq_ptrs,
+                 const int64_t* numel, const void* chunks, int n_chunks, int chunk_elems, const float* partials,
+                 float max_norm, float skip_above, float lr, float beta1, float beta2, float eps, int step,
+                 float* norm_out /* [2] */, void* stream);
 
 #ifdef __cplusplus
 }

@@ -20,6 +20,8 @@ LIB_PATH = os.environ.get("PG_B200_LIB") or os.path.join(_HERE, "libpg_b200.so")
 
 ACT_NONE, ACT_RELU, ACT_GELU, ACT_ELU, ACT_TANH = 0, 1, 2, 3, 4
 ACT_GIVEN = 5  # dact only: aux already holds the derivative
+ACT_RELU_OUT, ACT_ELU_OUT = 6, 7  # dact only: aux holds the activated value
+DACT_FROM_OUT = {ACT_RELU: ACT_RELU_OUT, ACT_ELU: ACT_ELU_OUT}
 ACT_STORE_DERIV = 0x100  # OR-ed into act: out_pre receives act'(pre)
 ACT_BY_NAME = {None: ACT_NONE, "none": ACT_NONE, "relu": ACT_RELU, "gelu": ACT_GELU, "elu": ACT_ELU, "tanh": ACT_TANH}
 
@@ -61,6 +63,7 @@ _SIGNATURES = {
     "pg_pm_to_nchw": [_vp, _i32, _i64, _i32, _i32, _i32, _i32, _vp, _vp],
     "pg_dact_mul": [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _vp, _i64, _vp],
     "pg_cast_f32_to_bf16": [_vp, _vp, _i64, _vp],
+    "pg_act_cast_bf16": [_vp, _i32, _i64, _i32, _i32, _i32, _vp, _i64, _vp],
     "pg_causal_attn_fwd": [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _i32, _i32, _vp],
     "pg_causal_attn_bwd": [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _i64,
                            _vp, _i64, _i32, _i32, _i32, _i32, _i32, _f32, _i32, _i32, _vp],
@@ -68,6 +71,8 @@ _SIGNATURES = {
     "pg_conv_small_bwd": [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp],
     "pg_attn_decode": [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i32, _i32, _i32, _i32, _i32,
                        _f32, _i32, _vp],
+    "pg_grad_sqnorm": [_vp, _vp, _vp, _i32, _i32, _vp, _vp],
+    "pg_adam_step": [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _f32, _f32, _f32, _f32, _f32, _f32, _i32, _vp, _vp],
     "pg_tap_gather": [_vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _vp],
     "pg_tap_scatter": [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _i64, _vp, _vp, _i64, _vp],
 }
@@ -357,6 +362,16 @@ def dact_mul(dy, pre, act, out):
 
 
 @_device_guarded
+def act_cast(x, act, out):
+    """out = bf16(act(x)); x: [P, C] fp32 or bf16 view, out: [P, C] bf16 view."""
+    lib = load()
+    (xp, ldx), (op, ldo) = _pm(x), _pm(out)
+    P, C = x.shape
+    assert out.dtype == torch.bfloat16 and out.shape == x.shape and x.dtype in (torch.float32, torch.bfloat16)
+    _check(lib.pg_act_cast_bf16(xp, int(x.dtype == torch.float32), ldx, P, C, act, op, ldo, _stream()), "pg_act_cast_bf16")
+
+
+@_device_guarded
 def cast_bf16(x, y):
     lib = load()
     assert x.dtype == torch.float32 and y.dtype == torch.bfloat16 and x.is_contiguous() and y.is_contiguous()
@@ -405,6 +420,20 @@ def conv_small_bwd(x, w, dy_pm, pad, dw=None, dbias=None, dx=None, pre_act=ACT_N
     assert dy_pm.dtype == torch.float32 and dy_pm.is_contiguous()
     _check(lib.pg_conv_small_bwd(_ptr(x), _ptr(w), _ptr(dy_pm), N, Cin, H, W, Cout, kh, kw, pad[0], pad[1], pre_act,
                                  _ptr(dw), _ptr(dbias), _ptr(dx), _stream()), "pg_conv_small_bwd")
+
+
+@_device_guarded
+def grad_sqnorm(grad_ptrs, numel, chunks, n_chunks, chunk_elems, partials):
+    _check(load().pg_grad_sqnorm(_ptr(grad_ptrs), _ptr(numel), _ptr(chunks), n_chunks, chunk_elems, _ptr(partials),
+                                 _stream()), "pg_grad_sqnorm")
+
+
+@_device_guarded
+def adam_step(param_ptrs, grad_ptrs, m_ptrs, v_ptrs, numel, chunks, n_chunks, chunk_elems, partials, max_norm, skip_above,
+              lr, beta1, beta2, eps, step, norm_out):
+    _check(load().pg_adam_step(_ptr(param_ptrs), _ptr(grad_ptrs), _ptr(m_ptrs), _ptr(v_ptrs), _ptr(numel), _ptr(chunks),
+                               n_chunks, chunk_elems, _ptr(partials), max_norm, skip_above, lr, beta1, beta2, eps, step,
+                               _ptr(norm_out), _stream()), "pg_adam_step")
 
 
 def _int_array(vals):

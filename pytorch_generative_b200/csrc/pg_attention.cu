@@ -8,6 +8,7 @@
 // impl 1 (this section): SIMT kernels, one warp per row — the on-device cross-check used by the tests.
 // impl 0: tensor-core kernels (pg_attention_tc.cuh), the product path.
 // impl 3 (backward only): the round-1 tensor-core kernel (one CTA per key tile), kept for A/B measurements.
+#include <stdlib.h>
 #include <type_traits>
 
 #include "../../include/pg_b200.h"
@@ -28,6 +29,7 @@ struct AttnArgs {
   float* dq_accum;
   int N, S, H, dk, dv, strict;
   float scale;
+  int dbg;  // PG_ATTN_DEBUG (timing experiments only): 1 = no MMAs issued, 2 = no softmax-thread arithmetic
 };
 
 // One warp per (image, head, query row).
@@ -325,6 +327,10 @@ extern "C" int pg_causal_attn_bwd(const void* q, int64_t ld_q, const void* k, in
   a.N = N; a.S = S; a.H = H; a.dk = dk; a.dv = dv; a.strict = strict;
   a.scale = scale;
   a.dq_accum = dq_accum;
+  {
+    static const char* dbg = getenv("PG_ATTN_DEBUG");
+    a.dbg = dbg ? atoi(dbg) : 0;
+  }
   const long long total = (long long)N * H * S;
   const int lanes_per = dv / 8;
   const bool pow2 = dv % 8 == 0 && lanes_per >= 1 && lanes_per <= 32 && (lanes_per & (lanes_per - 1)) == 0;

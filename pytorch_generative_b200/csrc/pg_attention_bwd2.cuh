@@ -12,11 +12,11 @@
 //         tensor   | dP(i) ..        | S(i+1), dV(i)     | dK(i), dP(i+1), dQ(i)| S(i+2), dV(i+1) ...
 //     S and dP stay single-buffered in TMEM (S is free again once every thread has read it = when P is published);
 //   * dQ is drained by its own warpgroup (TMEM -> fp32 staging slab -> TMA reduce-add), off the softmax threads;
-//   * the CTA is persistent: work items (longest first) are dealt round-robin to the grid, K/V of the next item and
+//   * the CTA is persistent: work items are dealt statically, balanced and L2-local (see Bwd2Cursor), K/V of the next item and
 //     Q / dO of the next tiles are prefetched through multi-stage rings, TMEM and barriers are set up once.
 //
 // Warp roles (448 threads): 0-3 softmax group A (key columns 0-63), 4-7 group B (64-127), thread = query row;
-// 8-11 dQ drain (thread = query row); 12 TMA producer; 13 TMEM owner + MMA issuer.
+// 8-11 dQ drain (thread = query row) + dV / dK read-out at the end of an item (thread = key row); 12 TMA producer; 13 TMEM owner + MMA issuer.
 #pragma once
 
 namespace {
@@ -42,31 +42,46 @@ struct Bwd2 {
   static_assert(SMEM <= 232448, "shared memory budget");
 };
 
-// Position in the CTA's work stream: item w = (key tile j, image n, head h), tile `it` of its T - j query tiles.
+// Position in the CTA's work stream: item = (key tile j, image n, head h), tile `it` of its T - j query tiles.
+//
+// Scheduling.  The grid is G groups of `slots` = ceil(T / 2) CTAs.  A group works on one (image, head) at a time
+// (group g takes nh = g, g + G, ...); CTA r of the group takes key tiles r and T - 1 - r of it, i.e. T + 1 query tiles
+// whatever r is, so the CTAs stay balanced, and the 148 CTAs touch only ~G (image, head) pairs at any time: Q, dO and
+// the fp32 dQ accumulator of those pairs (0.5 MB each at S = 1024) stay in L2 across the key tiles that re-read /
+// re-accumulate them.  (Dealing the items longest-first over the whole batch instead made every key tile re-stream
+// its pair's Q / dO / dQ from HBM: 1.9 GB of DRAM traffic per call at N = 64, profiles/r02_attn_bwd2_v1_ncu.txt.)
 struct Bwd2Cursor {
-  int w, n, h, j, niter, it;
+  int q;  // index in the CTA's item sequence: (round, sub) = (q / 2, q % 2)
+  int n, h, j, niter, it;
   bool valid;
 };
-__device__ __forceinline__ void bwd2_item(Bwd2Cursor& c, int w, const AttnArgs& a, int T) {
+__device__ __forceinline__ void bwd2_item(Bwd2Cursor& c, int q, const AttnArgs& a, int T) {
   const int NH = a.N * a.H;
-  c.w = w;
-  c.valid = w < NH * T;
+  const int slots = (T + 1) >> 1;
+  const int G = (int)gridDim.x / slots, grp = (int)blockIdx.x / slots, r = (int)blockIdx.x % slots;
   c.it = 0;
-  if (c.valid) {
-    const int nh = w % NH;
-    c.j = w / NH;  // small j first: the longest items are dealt first
+  for (;; ++q) {
+    const int nh = grp + G * (q >> 1);
+    c.q = q;
+    c.valid = nh < NH;
+    if (!c.valid) {
+      c.j = c.n = c.h = 0;
+      c.niter = 1;
+      return;
+    }
+    const int j = (q & 1) ? T - 1 - r : r;
+    if ((q & 1) && j == r) continue;  // odd T: the middle key tile has no partner
+    c.j = j;
     c.n = nh / a.H;
     c.h = nh % a.H;
-    c.niter = T - c.j;
-  } else {
-    c.j = c.n = c.h = 0;
-    c.niter = 1;
+    c.niter = T - j;
+    return;
   }
 }
 // returns true when the step crossed an item boundary
 __device__ __forceinline__ bool bwd2_next(Bwd2Cursor& c, const AttnArgs& a, int T) {
   if (++c.it < c.niter) return false;
-  bwd2_item(c, c.w + (int)gridDim.x, a, T);
+  bwd2_item(c, c.q + 1, a, T);
   return true;
 }
 
@@ -92,14 +107,14 @@ attn_bwd2_kernel(const __grid_constant__ AttnTmaps tm, const AttnArgs a, const i
   uint64_t* do_empty = bars + 12;      // [2]
   uint64_t* s_full = bars + 14;        // S of the tile complete in TMEM
   uint64_t* dp_full = bars + 15;       // dP ...
-  uint64_t* p_full = bars + 16;        // P in smem, S read by every softmax thread (256 arrivals)
-  uint64_t* ds_full = bars + 17;       // dS in smem, dP read (256 arrivals)
+  uint64_t* p_full = bars + 16;        // P in smem, S read by every softmax thread (8 warp arrivals)
+  uint64_t* ds_full = bars + 17;       // dS in smem, dP read (8 warp arrivals)
   uint64_t* p_free = bars + 18;        // dV product has finished reading P
   uint64_t* ds_free = bars + 19;       // dK and dQ products have finished reading dS
   uint64_t* dq_full = bars + 20;       // [2] dQ of the tile complete in TMEM
-  uint64_t* dq_empty = bars + 22;      // [2] ... drained (128 arrivals)
+  uint64_t* dq_empty = bars + 22;      // [2] ... drained (4 warp arrivals)
   uint64_t* acc_full = bars + 24;      // dV / dK of the item complete
-  uint64_t* acc_empty = bars + 25;     // ... read out (256 arrivals)
+  uint64_t* acc_empty = bars + 25;     // ... read out by the drain warpgroup (4 warp arrivals)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -109,13 +124,13 @@ attn_bwd2_kernel(const __grid_constant__ AttnTmaps tm, const AttnArgs a, const i
     for (int s = 0; s < 2; ++s) {
       mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1);
       mbar_init(&do_full[s], 1); mbar_init(&do_empty[s], 1);
-      mbar_init(&dq_full[s], 1); mbar_init(&dq_empty[s], 128);
+      mbar_init(&dq_full[s], 1); mbar_init(&dq_empty[s], 4);
     }
     for (int s = 0; s < 3; ++s) { mbar_init(&q_full[s], 1); mbar_init(&q_empty[s], 1); }
     mbar_init(s_full, 1); mbar_init(dp_full, 1);
-    mbar_init(p_full, 256); mbar_init(ds_full, 256);
+    mbar_init(p_full, 8); mbar_init(ds_full, 8);  // one elected arrival per softmax warp
     mbar_init(p_free, 1); mbar_init(ds_free, 1);
-    mbar_init(acc_full, 1); mbar_init(acc_empty, 256);
+    mbar_init(acc_full, 1); mbar_init(acc_empty, 4);
     fence_barrier_init();
     fence_proxy_async_smem();
   }
@@ -126,7 +141,7 @@ attn_bwd2_kernel(const __grid_constant__ AttnTmaps tm, const AttnArgs a, const i
   const uint32_t tmem = *tmem_slot;
 
   Bwd2Cursor c;
-  bwd2_item(c, (int)blockIdx.x, a, T);
+  bwd2_item(c, 0, a, T);
 
   if (warp == 12) {
     // ===================== TMA producer =====================
@@ -173,6 +188,7 @@ attn_bwd2_kernel(const __grid_constant__ AttnTmaps tm, const AttnArgs a, const i
         mbar_wait(&q_full[g % C::NQ], (g / C::NQ) & 1u);
         tc_fence_after();
         const uint32_t qa = q_of(g), ka = k_of(m);
+        if (a.dbg != 1)
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk)
           umma_bf16_ss(tmem + C::COL_S, desc_kmajor(qa, kk), desc_kmajor(ka, kk), idesc_s, kk > 0);
@@ -182,11 +198,13 @@ attn_bwd2_kernel(const __grid_constant__ AttnTmaps tm, const AttnArgs a, const i
         mbar_wait(&do_full[g % C::NDO], (g / C::NDO) & 1u);
         tc_fence_after();
         const uint32_t da = do_of(g), va = v_of(m);
+        if (a.dbg != 1)
 #pragma unroll
         for (int kk = 0; kk < DV / 16; ++kk)
           umma_bf16_ss(tmem + C::COL_DP, desc_kmajor(da, kk), desc_kmajor(va, kk), idesc_s, kk > 0);
         umma_commit(dp_full);
       };
+      const bool mma_on = a.dbg != 1;
       unsigned g = 0, m = 0;
       if (c.valid) {
         issue_s(0, 0, true);
@@ -208,6 +226,7 @@ attn_bwd2_kernel(const __grid_constant__ AttnTmaps tm, const AttnArgs a, const i
           mbar_wait(acc_empty, (m & 1u) ^ 1u);
           tc_fence_after();
         }
+        if (mma_on)
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)  // K = 128 queries
           umma_bf16_ss(tmem + C::COL_DV, desc_mnmajor(p_addr, kk), desc_mnmajor(da, kk), idesc_dv, (!first || kk > 0));
@@ -216,6 +235,7 @@ attn_bwd2_kernel(const __grid_constant__ AttnTmaps tm, const AttnArgs a, const i
 
         mbar_wait(ds_full, g & 1u);  // dS(g) published; dP is free
         tc_fence_after();
+        if (mma_on)
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)
           umma_bf16_ss(tmem + C::COL_DK, desc_mnmajor(ds_addr, kk), desc_mnmajor(qa, kk), idesc_dk, (!first || kk > 0));
@@ -224,6 +244,7 @@ attn_bwd2_kernel(const __grid_constant__ AttnTmaps tm, const AttnArgs a, const i
         const unsigned b = g % C::NDQ;
         mbar_wait(&dq_empty[b], ((g / C::NDQ) & 1u) ^ 1u);
         tc_fence_after();
+        if (mma_on)
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)  // K = 128 keys
           umma_bf16_ss(tmem + C::COL_DQ + b * 64, desc_kmajor(ds_addr, kk), desc_mnmajor(ka, kk), idesc_dq, kk > 0);
@@ -247,7 +268,7 @@ attn_bwd2_kernel(const __grid_constant__ AttnTmaps tm, const AttnArgs a, const i
     const int r = (warp & 3) * 32 + lane;
     const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
     const bool leader = threadIdx.x == 256;
-    unsigned g = 0;
+    unsigned g = 0, m = 0;
     while (c.valid) {
       const unsigned b = g % C::NDQ;
       const int i = c.j + c.it;
@@ -258,7 +279,8 @@ attn_bwd2_kernel(const __grid_constant__ AttnTmaps tm, const AttnArgs a, const i
       tmem_ld_32x32b_x32(tmem + C::COL_DQ + b * 64 + lane_base + 32, v1);
       tmem_wait_ld();
       tc_fence_before();
-      mbar_arrive(&dq_empty[b]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&dq_empty[b]);
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         if (leader) tma_store_wait_read<0>();  // the previous reduce has finished reading the slab
@@ -274,6 +296,49 @@ attn_bwd2_kernel(const __grid_constant__ AttnTmaps tm, const AttnArgs a, const i
         }
         __syncwarp();
       }
+      if (c.it == c.niter - 1) {
+        // ---- dV_j, dK_j read-out (thread == key row): off the softmax threads, which move on to the next item ----
+        mbar_wait(acc_full, m & 1u);
+        tc_fence_after();
+        const int kj = c.j * AT + r;
+        const bool key_ok = kj < a.S;
+        bf16* dvrow = a.dv_out + ((size_t)c.n * a.S + kj) * a.ld_dv + c.h * DV;
+#pragma unroll
+        for (int col = 0; col < DV; col += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tmem + C::COL_DV + lane_base + col, v);
+          tmem_wait_ld();
+          if (key_ok) {
+#pragma unroll
+            for (int e = 0; e < 32; e += 8)
+              *reinterpret_cast<uint4*>(dvrow + col + e) =
+                  make_uint4(pack_bf16x2(__uint_as_float(v[e]), __uint_as_float(v[e + 1])),
+                             pack_bf16x2(__uint_as_float(v[e + 2]), __uint_as_float(v[e + 3])),
+                             pack_bf16x2(__uint_as_float(v[e + 4]), __uint_as_float(v[e + 5])),
+                             pack_bf16x2(__uint_as_float(v[e + 6]), __uint_as_float(v[e + 7])));
+          }
+        }
+        bf16* dkrow = a.dk_out + ((size_t)c.n * a.S + kj) * a.ld_dk + c.h * 64;
+#pragma unroll
+        for (int col = 0; col < 64; col += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tmem + C::COL_DK + lane_base + col, v);
+          tmem_wait_ld();
+          if (key_ok) {
+#pragma unroll
+            for (int e = 0; e < 32; e += 8)
+              *reinterpret_cast<uint4*>(dkrow + col + e) = make_uint4(
+                  pack_bf16x2(__uint_as_float(v[e]) * a.scale, __uint_as_float(v[e + 1]) * a.scale),
+                  pack_bf16x2(__uint_as_float(v[e + 2]) * a.scale, __uint_as_float(v[e + 3]) * a.scale),
+                  pack_bf16x2(__uint_as_float(v[e + 4]) * a.scale, __uint_as_float(v[e + 5]) * a.scale),
+                  pack_bf16x2(__uint_as_float(v[e + 6]) * a.scale, __uint_as_float(v[e + 7]) * a.scale));
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty);
+        ++m;
+      }
       ++g;
       bwd2_next(c, a, T);
     }
@@ -285,7 +350,7 @@ attn_bwd2_kernel(const __grid_constant__ AttnTmaps tm, const AttnArgs a, const i
     const int r = (warp & 3) * 32 + lane;   // TMEM lane / tile row
     const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
     const float sl2 = a.scale * 1.4426950408889634f;
-    unsigned g = 0, m = 0;
+    unsigned g = 0;
     float lse_next = 0.f, delta_next = 0.f;
     auto load_stats = [&](const Bwd2Cursor& cc) {
       lse_next = 0.f;
@@ -309,7 +374,6 @@ attn_bwd2_kernel(const __grid_constant__ AttnTmaps tm, const AttnArgs a, const i
       const float delta = delta_next;
       const int qlim = row_ok ? qi - a.strict : -1;  // invalid rows see no keys
       const bool need_mask = (c.it == 0) || (i == T - 1);
-      const bool last = c.it == c.niter - 1;
       Bwd2Cursor nx = c;
       bwd2_next(nx, a, T);
       load_stats(nx);  // in flight underneath this tile
@@ -318,7 +382,8 @@ attn_bwd2_kernel(const __grid_constant__ AttnTmaps tm, const AttnArgs a, const i
       mbar_wait(s_full, g & 1u);
       tc_fence_after();
       uint32_t pk[2][16];
-      {
+      const bool work = a.dbg != 2;
+      if (work) {
         uint32_t sv[2][32];
         tmem_ld_32x32b_x32(tmem + C::COL_S + lane_base + (grp * 2) * 32, sv[0]);
         tmem_ld_32x32b_x32(tmem + C::COL_S + lane_base + (grp * 2 + 1) * 32, sv[1]);
@@ -344,16 +409,19 @@ attn_bwd2_kernel(const __grid_constant__ AttnTmaps tm, const AttnArgs a, const i
         else p_tile(std::false_type{});
       }
       if (g > 0) mbar_wait(p_free, (g - 1) & 1u);  // dV(g-1) no longer reads sP
-      store_tile_row_chunk(sP, r, grp * 2, pk[0]);
-      store_tile_row_chunk(sP, r, grp * 2 + 1, pk[1]);
+      if (work) {
+        store_tile_row_chunk(sP, r, grp * 2, pk[0]);
+        store_tile_row_chunk(sP, r, grp * 2 + 1, pk[1]);
+      }
       fence_proxy_async_smem();
       tc_fence_before();
-      mbar_arrive(p_full);
+      __syncwarp();  // one arrival per warp: every arrival wakes the warps parked on this SM's barriers
+      if (lane == 0) mbar_arrive(p_full);
 
       // ---- stage B: dP -> dS = P (dP - delta) ----
       mbar_wait(dp_full, g & 1u);
       tc_fence_after();
-      {
+      if (work) {
         uint32_t dv[2][32];
         tmem_ld_32x32b_x32(tmem + C::COL_DP + lane_base + (grp * 2) * 32, dv[0]);
         tmem_ld_32x32b_x32(tmem + C::COL_DP + lane_base + (grp * 2 + 1) * 32, dv[1]);
@@ -370,55 +438,15 @@ attn_bwd2_kernel(const __grid_constant__ AttnTmaps tm, const AttnArgs a, const i
         }
       }
       if (g > 0) mbar_wait(ds_free, (g - 1) & 1u);  // dK(g-1), dQ(g-1) no longer read sdS
-      store_tile_row_chunk(sdS, r, grp * 2, pk[0]);
-      store_tile_row_chunk(sdS, r, grp * 2 + 1, pk[1]);
+      if (work) {
+        store_tile_row_chunk(sdS, r, grp * 2, pk[0]);
+        store_tile_row_chunk(sdS, r, grp * 2 + 1, pk[1]);
+      }
       fence_proxy_async_smem();
       tc_fence_before();
-      mbar_arrive(ds_full);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ds_full);
 
-      if (last) {
-        // ---- dV_j, dK_j read-out: thread == key row, each group writes its half of the columns ----
-        mbar_wait(acc_full, m & 1u);
-        tc_fence_after();
-        const int kj = k0 + r;
-        const bool key_ok = kj < a.S;
-        bf16* dvrow = a.dv_out + ((size_t)c.n * a.S + kj) * a.ld_dv + c.h * DV;
-#pragma unroll
-        for (int cc = 0; cc < DV / 64; ++cc) {
-          const int col = (grp * (DV / 64) + cc) * 32;
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(tmem + C::COL_DV + lane_base + col, v);
-          tmem_wait_ld();
-          if (key_ok) {
-#pragma unroll
-            for (int e = 0; e < 32; e += 8)
-              *reinterpret_cast<uint4*>(dvrow + col + e) =
-                  make_uint4(pack_bf16x2(__uint_as_float(v[e]), __uint_as_float(v[e + 1])),
-                             pack_bf16x2(__uint_as_float(v[e + 2]), __uint_as_float(v[e + 3])),
-                             pack_bf16x2(__uint_as_float(v[e + 4]), __uint_as_float(v[e + 5])),
-                             pack_bf16x2(__uint_as_float(v[e + 6]), __uint_as_float(v[e + 7])));
-          }
-        }
-        bf16* dkrow = a.dk_out + ((size_t)c.n * a.S + kj) * a.ld_dk + c.h * 64;
-        {
-          const int col = grp * 32;
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(tmem + C::COL_DK + lane_base + col, v);
-          tmem_wait_ld();
-          if (key_ok) {
-#pragma unroll
-            for (int e = 0; e < 32; e += 8)
-              *reinterpret_cast<uint4*>(dkrow + col + e) = make_uint4(
-                  pack_bf16x2(__uint_as_float(v[e]) * a.scale, __uint_as_float(v[e + 1]) * a.scale),
-                  pack_bf16x2(__uint_as_float(v[e + 2]) * a.scale, __uint_as_float(v[e + 3]) * a.scale),
-                  pack_bf16x2(__uint_as_float(v[e + 4]) * a.scale, __uint_as_float(v[e + 5]) * a.scale),
-                  pack_bf16x2(__uint_as_float(v[e + 6]) * a.scale, __uint_as_float(v[e + 7]) * a.scale));
-          }
-        }
-        tc_fence_before();
-        mbar_arrive(acc_empty);
-        ++m;
-      }
       c = nx;
       ++g;
     }
@@ -447,8 +475,11 @@ int attn_bwd_tc2(const AttnArgs& a, cudaStream_t stream) {
     if (pg_make_tmap_nd(&tm.dq, a.dq_accum, 4, 3, dims, strides, box, 128)) return 1;
   }
   const int T = (a.S + AT - 1) / AT;
-  const int items = a.N * a.H * T;
-  const unsigned grid = (unsigned)(items < pg_num_sms() ? items : pg_num_sms());
+  const int slots = (T + 1) / 2;  // CTAs per (image, head) group, see Bwd2Cursor
+  int groups = pg_num_sms() / slots;
+  if (groups > a.N * a.H) groups = a.N * a.H;
+  if (groups < 1) groups = 1;
+  const unsigned grid = (unsigned)(groups * slots);
   if (a.dv == 64) {
     PG_CUDA(cudaFuncSetAttribute(attn_bwd2_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, Bwd2<64>::SMEM));
     attn_bwd2_kernel<64><<<grid, 448, Bwd2<64>::SMEM, stream>>>(tm, a, T);

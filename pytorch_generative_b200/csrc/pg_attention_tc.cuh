@@ -106,8 +106,10 @@ attn_fwd_tc_kernel(const __grid_constant__ AttnTmaps tm, const AttnArgs a, const
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nh = blockIdx.x % (a.N * a.H);
-  const int i = T - 1 - blockIdx.x / (a.N * a.H);  // longest rows first
+  // consecutive blocks = the query tiles of one (image, head), longest first: the ~300 co-resident CTAs then share
+  // the K / V of ~37 pairs through L2 instead of every query tile streaming its keys from HBM
+  const int nh = blockIdx.x / T;
+  const int i = T - 1 - blockIdx.x % T;
   const int n = nh / a.H, h = nh % a.H;
   const int ntiles = i + 1;
 
@@ -116,7 +118,7 @@ attn_fwd_tc_kernel(const __grid_constant__ AttnTmaps tm, const AttnArgs a, const
     mbar_init(q_full, 1);
     for (int s = 0; s < 2; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
     mbar_init(s_full, 1);
-    mbar_init(p_full, 128);
+    mbar_init(p_full, 4);  // one elected arrival per softmax warp
     mbar_init(o_full, 1);
     fence_barrier_init();
     fence_proxy_async_smem();
@@ -277,7 +279,8 @@ attn_fwd_tc_kernel(const __grid_constant__ AttnTmaps tm, const AttnArgs a, const
       else softmax_tile(std::false_type{});
       fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
       tc_fence_before();
-      mbar_arrive(p_full);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
       // off the critical path (the tensor core is computing S(j+1) now): O = (O + PV(j-1)) * alpha_j
       if (j > 0) fold_pv(j - 1);
       l = l * alpha + lt;

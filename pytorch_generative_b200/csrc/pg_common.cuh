@@ -109,12 +109,67 @@ __device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parit
       : "memory");
   return ok != 0;
 }
+// Up to 256 try_waits in one tight PTX loop (3 instructions per wake-up).  PG_MBAR_SUSPEND_NS > 0 passes a
+// suspend-time hint (the warp may be parked that long: cheap for the issue slots, slow to wake -- measured as ~1 k
+// cycles per hand-off in the attention kernels); 0 uses try_wait's default (short) suspension; PG_MBAR_SPIN polls
+// with test_wait and never suspends.
+__device__ __forceinline__ bool mbar_wait_round(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+#if defined(PG_MBAR_SPIN)
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .u32 n;\n\t"
+      "mov.u32 n, 0;\n"
+      "PG_WAIT_LOOP:\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "@p bra PG_WAIT_DONE;\n\t"
+      "add.u32 n, n, 1;\n\t"
+      "setp.lt.u32 p, n, 4096;\n\t"
+      "@p bra PG_WAIT_LOOP;\n\t"
+      "setp.ne.u32 p, n, n;\n"
+      "PG_WAIT_DONE:\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+#elif PG_MBAR_SUSPEND_NS > 0
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .u32 n;\n\t"
+      "mov.u32 n, 0;\n"
+      "PG_WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "@p bra PG_WAIT_DONE;\n\t"
+      "add.u32 n, n, 1;\n\t"
+      "setp.lt.u32 p, n, 256;\n\t"
+      "@p bra PG_WAIT_LOOP;\n\t"
+      "setp.ne.u32 p, n, n;\n"
+      "PG_WAIT_DONE:\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)PG_MBAR_SUSPEND_NS)
+      : "memory");
+#else
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .u32 n;\n\t"
+      "mov.u32 n, 0;\n"
+      "PG_WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "@p bra PG_WAIT_DONE;\n\t"
+      "add.u32 n, n, 1;\n\t"
+      "setp.lt.u32 p, n, 1024;\n\t"
+      "@p bra PG_WAIT_LOOP;\n\t"
+      "setp.ne.u32 p, n, n;\n"
+      "PG_WAIT_DONE:\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+#endif
+  return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   long long t0 = 0;
-  uint32_t spins = 0;
-  while (!(PG_MBAR_SUSPEND_NS ? mbar_try_wait_hint(bar, parity, PG_MBAR_SUSPEND_NS) : mbar_try_wait(bar, parity))) {
-    if ((++spins & 255u) != 0) continue;  // the clock is only read every 256 wake-ups
+  while (!mbar_wait_round(bar, parity)) {  // the clock is only read every 256 wake-ups
     if (t0 == 0) {
       t0 = clock64();
     } else if (clock64() - t0 > PG_MBAR_TIMEOUT_CYCLES) {
@@ -423,6 +478,8 @@ __device__ __forceinline__ float pg_act_bwd(int act, float x) {
       return 1.f - t * t;
     }
     case PG_ACT_GIVEN: return x;  // the operand already is the derivative
+    case PG_ACT_RELU_OUT: return x > 0.f ? 1.f : 0.f;      // x = relu(pre)
+    case PG_ACT_ELU_OUT: return x > 0.f ? 1.f : x + 1.f;   // x = elu(pre): elu'(pre) = e^pre = elu(pre) + 1 for pre <= 0
     default: return 1.f;
   }
 }

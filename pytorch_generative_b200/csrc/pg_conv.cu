@@ -75,7 +75,7 @@ constexpr int WG_MAX_OUT_PER_THREAD = 64;
 
 __global__ void __launch_bounds__(256)
 conv_small_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, const ConvArgs a,
-                        float* __restrict__ dw) {
+                        float* __restrict__ dw, const int o_base) {
   extern __shared__ float smw[];
   float* patch = smw;                          // [WG_PIX][K]
   float* dys = smw + WG_PIX * a.K;             // [WG_PIX][Cout]
@@ -105,7 +105,7 @@ conv_small_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ d
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < WG_MAX_OUT_PER_THREAD; ++i) {
-      const int o = threadIdx.x + i * blockDim.x;
+      const int o = o_base + threadIdx.x + i * blockDim.x;
       if (o < n_out) {
         const int co = o / a.K, k = o % a.K;
         float s = 0.f;
@@ -117,7 +117,7 @@ conv_small_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ d
   }
 #pragma unroll
   for (int i = 0; i < WG_MAX_OUT_PER_THREAD; ++i) {
-    const int o = threadIdx.x + i * blockDim.x;
+    const int o = o_base + threadIdx.x + i * blockDim.x;
     if (o < n_out) atomicAdd(dw + o, acc[i]);
   }
 }
@@ -300,15 +300,17 @@ extern "C" int pg_conv_small_bwd(const float* x_nchw, const float* w_oihw, const
   PG_REQUIRE(a.K <= MAX_K, "pg_conv_small_bwd: Cin*kh*kw = %d exceeds %d", a.K, MAX_K);
   const long long P = (long long)N * H * W;
   if (dw_oihw) {
-    PG_REQUIRE(a.Cout * a.K <= WG_MAX_OUT_PER_THREAD * 256, "pg_conv_small_bwd: Cout*K = %d too large", a.Cout * a.K);
     const size_t smem = (size_t)WG_PIX * (a.K + a.Cout) * sizeof(float);
     PG_REQUIRE(smem <= 200 * 1024, "pg_conv_small_bwd: shared memory %zu too large", smem);
     PG_CUDA(cudaFuncSetAttribute(conv_small_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     long long blocks = (P + WG_PIX - 1) / WG_PIX;
     const long long cap = (long long)pg_num_sms() * 2;
     if (blocks > cap) blocks = cap;
-    conv_small_wgrad_kernel<<<(unsigned)blocks, 256, smem, stream>>>(x_nchw, dy_pm, a, dw_oihw);
-    if (pg_check_launch("pg_conv_small_bwd(wgrad)")) return 1;
+    // each launch covers WG_MAX_OUT_PER_THREAD * 256 = 16384 of the Cout*K outputs (one launch at every BASELINE config)
+    for (int o_base = 0; o_base < a.Cout * a.K; o_base += WG_MAX_OUT_PER_THREAD * 256) {
+      conv_small_wgrad_kernel<<<(unsigned)blocks, 256, smem, stream>>>(x_nchw, dy_pm, a, dw_oihw, o_base);
+      if (pg_check_launch("pg_conv_small_bwd(wgrad)")) return 1;
+    }
   }
   if (dbias) {
     if (pg_colsum_f32(dy_pm, Cout, (int)P, Cout, dbias, 1, stream_)) return 1;

@@ -482,6 +482,40 @@ __global__ void cast_kernel(const float* __restrict__ x, bf16* __restrict__ y, l
     y[i] = __float2bfloat16(x[i]);
 }
 
+// out = bf16(act(x)) over a pitched [P, C] matrix, 8 elements (one 16-byte store) per thread.
+template <typename TI>
+__global__ void __launch_bounds__(256)
+act_cast_kernel(const TI* __restrict__ x, int64_t ld_x, int P, int C, int act, bf16* __restrict__ out, int64_t ld_out) {
+  const int c8n = C / 8;
+  const long long total = (long long)P * c8n;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long row = idx / c8n;
+    const int c = (int)(idx % c8n) * 8;
+    float v[8];
+    if constexpr (sizeof(TI) == 4) {
+      const float4 a = *reinterpret_cast<const float4*>(x + row * ld_x + c);
+      const float4 b = *reinterpret_cast<const float4*>(x + row * ld_x + c + 4);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+      const uint4 a = *reinterpret_cast<const uint4*>(x + row * ld_x + c);
+      const uint32_t w[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = unpack_bf16x2(w[i]);
+        v[2 * i] = f.x;
+        v[2 * i + 1] = f.y;
+      }
+    }
+    if (act != PG_ACT_NONE) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = pg_act_fwd(act, v[i]);
+    }
+    *reinterpret_cast<uint4*>(out + row * ld_out + c) =
+        make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+  }
+}
+
 int grid_for(long long work_items, int threads, int max_blocks_per_sm = 16) {
   long long b = (work_items + threads - 1) / threads;
   long long cap = (long long)pg_num_sms() * max_blocks_per_sm;
@@ -661,4 +695,15 @@ extern "C" int pg_dact_mul(const void* dy_bf16, int64_t ld_dy, const float* pre_
   dact_mul_kernel<<<grid_for((long long)P * C, 256), 256, 0, stream>>>((const bf16*)dy_bf16, ld_dy, pre_f32, ld_pre, P, C, act,
                                                                       (bf16*)out_bf16, ld_out);
   return pg_check_launch("pg_dact_mul");
+}
+
+extern "C" int pg_act_cast_bf16(const void* x, int x_is_f32, int64_t ld_x, int P, int C, int act, void* out_bf16,
+                                int64_t ld_out, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  PG_REQUIRE(x && out_bf16 && P > 0 && C > 0, "pg_act_cast_bf16: null/empty argument");
+  PG_REQUIRE(C % 8 == 0 && ld_x % (x_is_f32 ? 4 : 8) == 0 && ld_out % 8 == 0, "pg_act_cast_bf16: C, pitches must be multiples of 8");
+  const int grid = grid_for((long long)P * (C / 8), 256);
+  if (x_is_f32) act_cast_kernel<float><<<grid, 256, 0, stream>>>((const float*)x, ld_x, P, C, act, (bf16*)out_bf16, ld_out);
+  else act_cast_kernel<bf16><<<grid, 256, 0, stream>>>((const bf16*)x, ld_x, P, C, act, (bf16*)out_bf16, ld_out);
+  return pg_check_launch("pg_act_cast_bf16");
 }

@@ -6,13 +6,16 @@ convolutions with extra padding followed by a front crop; here each such conv is
 encode pad + crop (no padded rows are ever computed), contracted on the tensor cores.
 """
 
+import os
+
 from torch import nn
 
 from .. import _lib as L
 from .. import nn as pg_nn
+from ..nn import pm
 from . import base
 
-RELU = L.ACT_RELU
+RELU, TANH, NONE = L.ACT_RELU, L.ACT_TANH, L.ACT_NONE
 
 
 class GatedPixelCNNLayer(nn.Module):
@@ -38,6 +41,34 @@ class GatedPixelCNNLayer(nn.Module):
                                            padding=(0, p + int(mask_center)))
         self._hstack_residual = pg_nn.TapConv2d(out_channels, out_channels, kernel_size=1)
         self._hstack_skip = pg_nn.TapConv2d(out_channels, out_channels, kernel_size=1)
+
+    def forward_pm(self, geom, v_b, h_f, h_b, skips, image=None):
+        """One layer on pixel-major tensors (the fused stack; same arithmetic as `forward`).
+
+        v_b: vertical stack, bf16 [P, C];  h_f / h_b: horizontal stack as fp32 stream and its bf16 copy;  skips: running
+        fp32 sum of the skip outputs (or None).  The causal input layer reads the NCHW `image` instead (3 channels: its
+        convolutions run on the direct fp32 kernel).  Every `+` of the reference layer is a GEMM-epilogue residual:
+        v + 1x1(v_in), link + 1xN(h_in), skips + skip, h + h_in."""
+        p, c = self._padding, self._out_channels
+        if image is not None:
+            v1 = pm.act_cast(pm.small_conv(image, self._vstack_1xN.weight, self._vstack_1xN.bias, (0, p)))
+        else:
+            v1, _ = pm.conv(v_b, self._vstack_1xN.weight, self._vstack_1xN.bias, geom, (0, p))
+        v2_f, v2_b = pm.conv(v1, self._vstack_Nx1.weight, self._vstack_Nx1.bias, geom, (p + 1, 0), emit=NONE, out_f32=True)
+        link, _ = pm.conv(v2_f, self._link.weight, self._link.bias, geom, xa=v2_b, out_f32=True)
+        if image is not None:
+            vv = v2_f + pm.small_conv(image, self._vstack_1x1.weight, self._vstack_1x1.bias, (0, 0))
+            hh = link + pm.small_conv(image, self._hstack_1xN.weight, self._hstack_1xN.bias, (0, p + int(self._mask_center)))
+        else:
+            vv, _ = pm.conv(v_b, self._vstack_1x1.weight, self._vstack_1x1.bias, geom, res=v2_f)
+            hh, _ = pm.conv(h_f, self._hstack_1xN.weight, self._hstack_1xN.bias, geom, (0, p + int(self._mask_center)),
+                            xa=h_b, res=link)
+        v_out = pm.gated(vv, TANH)
+        hs = pm.gated(hh, TANH)
+        skips, _ = pm.conv(hs, self._hstack_skip.weight, self._hstack_skip.bias, geom, res=skips, out_f32=True)
+        h_f, h_b = pm.conv(hs, self._hstack_residual.weight, self._hstack_residual.bias, geom,
+                           res=None if self._mask_center else h_f, emit=NONE, out_f32=True)
+        return v_out, h_f, h_b, skips
 
     def forward(self, vstack_input, hstack_input):
         vstack = self._vstack_Nx1(self._vstack_1xN(vstack_input))  # TapConv2d output == the reference's [:h] crop
@@ -69,10 +100,36 @@ class GatedPixelCNN(base.AutoregressiveModel):
             pg_nn.TapConv2d(in_channels=head_channels, out_channels=out_channels, kernel_size=1),
         )
 
+    def _forward_pm(self, x):
+        """The whole network on pixel-major tensors: NCHW only at the image and at the logits."""
+        n, _, h, w = x.shape
+        geom = pm.Geom(n, h, w)
+        v_b, h_f, h_b, skips = self._input.forward_pm(geom, None, None, None, None, image=x)
+        for layer in self._gated_layers:
+            v_b, h_f, h_b, skips = layer.forward_pm(geom, v_b, h_f, h_b, skips)
+        t, t_a = pm.conv(skips, self._head[1].weight, self._head[1].bias, geom, in_act=RELU, emit=RELU,
+                         emit_mode=pm.PRE_GRAD, want_main=False)
+        logits, _ = pm.conv(t_a, self._head[3].weight, self._head[3].bias, geom, in_act=RELU, xa=t_a, out_f32=True)
+        return pm.from_pm(logits, geom, self._head[3].weight.shape[0])
+
+    def _pm_ok(self, x):
+        c = self._gated_layers[0]._out_channels if len(self._gated_layers) else self._input._out_channels
+        return (x.is_cuda and os.environ.get("PG_NO_PM_STACK") != "1" and x.shape[1] * 7 <= 160
+                and pm.supported(x.shape[2], x.shape[3], (c, 2 * c)))
+
     def forward(self, x):
+        if self._pm_ok(x):
+            return self._forward_pm(x)
         vstack, hstack, skip_connections = self._input(x, x)
         for gated_layer in self._gated_layers:
             vstack, hstack, skip = gated_layer(vstack, hstack)
             skip_connections = skip_connections + skip
         t = self._head[1](skip_connections, pre_act=RELU)
         return self._head[3](t, pre_act=RELU)
+
+
+def reproduce(*args, **kwargs):
+    """The recipe of this model (reference gated_pixel_cnn.py `reproduce`); see `pytorch_generative_b200.recipes`."""
+    from .. import recipes
+
+    return recipes.reproduce_gated_pixel_cnn(*args, **kwargs)

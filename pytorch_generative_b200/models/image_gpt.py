@@ -388,3 +388,10 @@ class ImageGPT(base.AutoregressiveModel):
             flat.extend(blk.flat_params())
         flat.extend([self._ln.weight, self._ln.bias, self._out.weight, self._out.bias])
         return _ImageGPTStack.apply(x.float(), self._n_heads, self._ln.eps, *flat)
+
+
+def reproduce(*args, **kwargs):
+    """The recipe of this model (reference image_gpt.py `reproduce`); see `pytorch_generative_b200.recipes`."""
+    from .. import recipes
+
+    return recipes.reproduce_image_gpt(*args, **kwargs)

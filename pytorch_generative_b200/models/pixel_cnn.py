@@ -60,3 +60,10 @@ class PixelCNN(base.AutoregressiveModel):
             x = x + layer(x)  # the reference's second residual (pixel_cnn.py:109 on top of :53)
         x = self._head[1](x, pre_act=RELU)
         return self._head[3](x, pre_act=RELU)
+
+
+def reproduce(*args, **kwargs):
+    """The recipe of this model (reference pixel_cnn.py `reproduce`); see `pytorch_generative_b200.recipes`."""
+    from .. import recipes
+
+    return recipes.reproduce_pixel_cnn(*args, **kwargs)

@@ -6,14 +6,18 @@ convolutions with pad 1 + crop are tap lists {(-1,-1),(-1,0),(0,-1),(0,0)} on th
 fused into the conv that consumes or produces it (`pre_act` / `post_act`); the gate uses the identity activation.
 """
 
+import os
+
 import torch
 from torch import nn
 
 from .. import _lib as L
 from .. import nn as pg_nn
+from .. import ops
+from ..nn import pm
 from . import base
 
-ELU = L.ACT_ELU
+ELU, NONE = L.ACT_ELU, L.ACT_NONE
 
 
 class ResidualBlock(nn.Module):
@@ -24,6 +28,15 @@ class ResidualBlock(nn.Module):
         self._input_conv = pg_nn.TapConv2d(n_channels, n_channels, kernel_size=2, padding=1)
         self._output_conv = pg_nn.TapConv2d(n_channels, 2 * n_channels, kernel_size=2, padding=1)
         self._activation = pg_nn.GatedActivation(activation_fn=nn.Identity())
+
+    def forward_pm(self, geom, x_f, x_e=None):
+        """Pixel-major: x_f fp32 stream [P, C] (x_e = bf16 elu(x_f) when a producer already emitted it) -> fp32 stream.
+        conv -> elu -> conv runs as two tap-loop GEMMs: the first one's epilogue writes elu(.) only, the second one's
+        dgrad epilogue applies elu'."""
+        _, t = pm.conv(x_f, self._input_conv.weight, self._input_conv.bias, geom, (1, 1), in_act=ELU, xa=x_e, emit=ELU,
+                       emit_mode=pm.PRE_GRAD, want_main=False)
+        u, _ = pm.conv(t, self._output_conv.weight, self._output_conv.bias, geom, (1, 1), in_act=ELU, xa=t)
+        return x_f + pm.gated(u, NONE)
 
     def forward(self, x):
         out = self._input_conv(x, pre_act=ELU)       # conv(elu(x)), cropped to h x w
@@ -55,6 +68,23 @@ class PixelSNAILBlock(nn.Module):
         if key not in self._pos_cache:  # same values as the reference's image_positional_encoding, kept on device
             self._pos_cache[key] = pg_nn.image_positional_encoding(tuple(shape)).to(device)
         return self._pos_cache[key]
+
+    def forward_pm(self, geom, x_f, img_b, pos_b, pad_b, c_img):
+        """Pixel-major block: x_f fp32 stream [P, C]; img_b / pos_b bf16 [P, c_img] / [P, 2]; returns the block output
+        (to be added to the stream)."""
+        res = x_f
+        for rb in self._residual:
+            res = rb.forward_pm(geom, res)
+        c = res.shape[1]
+        a_kv = torch.cat((pos_b, pm.act_cast(res), img_b, pad_b), dim=1)  # [pos | features | image | 0-pad], bf16
+        attn = self._attention.forward_pm(a_kv, geom, c + 2, c_img)       # fp32 [P, value channels]
+        _, r = pm.conv(res, self._residual_out.weight, self._residual_out.bias, geom, in_act=ELU, emit=ELU,
+                       emit_mode=pm.POST, want_main=False)
+        _, a = pm.conv(attn, self._attention_out.weight, self._attention_out.bias, geom, in_act=ELU, emit=ELU,
+                       emit_mode=pm.POST, want_main=False)
+        _, out = pm.conv(r + a, self._out.weight, self._out.bias, geom, in_act=ELU, emit=ELU, emit_mode=pm.POST,
+                         want_main=False)
+        return out
 
     def forward(self, x, input_img):
         res = self._residual(x)
@@ -88,9 +118,42 @@ class PixelSNAIL(base.AutoregressiveModel):
             pg_nn.TapConv2d(in_channels=n_channels // 2, out_channels=out_channels, kernel_size=1),
         )
 
+    def _forward_pm(self, x):
+        """The whole network on pixel-major tensors: NCHW only at the image and at the logits."""
+        n, c_img, h, w = x.shape
+        geom = pm.Geom(n, h, w)
+        self._input.weight.data *= self._input.mask  # CausalConv2d's in-place masking (reference nn/convolution.py:42)
+        kh, kw = self._input.weight.shape[2:]
+        s = pm.small_conv(x, self._input.weight, self._input.bias, (kh // 2, kw // 2))  # fp32 stream [P, C]
+        blk0 = self._pixel_snail_blocks[0]
+        pos_b = ops.nchw_to_pm(blk0._positions(x.shape, x.device), torch.bfloat16)
+        img_b = ops.nchw_to_pm(x, torch.bfloat16)
+        width = ops.round_up(2 + s.shape[1] + c_img, 8)
+        pad_b = torch.zeros(n * h * w, width - (2 + s.shape[1] + c_img), dtype=torch.bfloat16, device=x.device)
+        for block in self._pixel_snail_blocks:
+            s = s + block.forward_pm(geom, s, img_b, pos_b, pad_b, c_img)
+        t, _ = pm.conv(s, self._output[0].weight, self._output[0].bias, geom)
+        logits, _ = pm.conv(t, self._output[1].weight, self._output[1].bias, geom, out_f32=True)
+        return pm.from_pm(logits, geom, self._output[1].weight.shape[0])
+
+    def _pm_ok(self, x):
+        c = self._input.weight.shape[0]
+        kh, kw = self._input.weight.shape[2:]
+        return (x.is_cuda and os.environ.get("PG_NO_PM_STACK") != "1" and x.shape[1] * kh * kw <= 160
+                and pm.supported(x.shape[2], x.shape[3], (c,)))
+
     def forward(self, x):
+        if self._pm_ok(x):
+            return self._forward_pm(x)
         input_img = x
         x = self._input(x)
         for block in self._pixel_snail_blocks:
             x = x + block(x, input_img)
         return self._output[1](self._output[0](x))
+
+
+def reproduce(*args, **kwargs):
+    """The recipe of this model (reference pixel_snail.py `reproduce`); see `pytorch_generative_b200.recipes`."""
+    from .. import recipes
+
+    return recipes.reproduce_pixel_snail(*args, **kwargs)

@@ -81,9 +81,10 @@ class CausalConv2d(nn.Conv2d):
             raise NotImplementedError("CausalConv2d: only stride 1, dilation 1, groups 1, zero padding are on the path")
         if pad != (kh // 2, kw // 2):
             raise NotImplementedError("CausalConv2d: only 'same' padding (k//2) is on the path")
-        if cin * kh * kw <= 160:
+        from .tapconv import small_conv_ok, tap_conv2d  # wide-channel masked convs run as a tap list on the tcgen05 GEMM
+
+        if small_conv_ok(self.weight.shape):
             return _SmallConvFn.apply(x, self.weight, self.bias, pad, pre_act)
-        from .tapconv import tap_conv2d  # wide-channel masked convs run as a tap list on the tcgen05 GEMM
 
         return tap_conv2d(x, self.weight, self.bias, pad, pre_act=pre_act)
 
@@ -312,6 +313,82 @@ class _AttentionFn(torch.autograd.Function):
         return (dx, dextra, g_qw, dbq[rq], g_kvw, torch.cat((dbkv[rq], dbkv[rv])), g_pw, dp_b, None, None, None, None)
 
 
+class _AttentionPMFn(torch.autograd.Function):
+    """The same attention block on a pixel-major operand: a_kv = [x | extra | 0-pad] bf16 [P, ckv_p] in, fp32 [P, out] out
+    (the fused conv stacks build a_kv once and never leave the pixel-major layout)."""
+
+    @staticmethod
+    def forward(ctx, a_kv, q_w, q_b, kv_w, kv_b, p_w, p_b, n_heads, embed, out_ch, strict, geom, cin, ce):
+        n, h, w = geom
+        S, H = h * w, n_heads
+        cin_p = ops.round_up(cin, 8)
+        ckv_p = a_kv.shape[1]
+        wq, bq, wkv, bkv, meta = pack_qkv_weights(q_w, q_b, kv_w, kv_b, H, embed, out_ch, cin_p, ckv_p)
+        dv_slot = meta["dv_slot"]
+        q, _, _ = ops.linear_fwd(a_kv[:, :cin_p], wq, bq)
+        kv, _, _ = ops.linear_fwd(a_kv, wkv, bkv)
+        k, v = kv[:, : H * ops.HEAD_SLOT], kv[:, H * ops.HEAD_SLOT:]
+        o, lse = ops.attn_fwd(q, k, v, n, S, H, meta["dk"], dv_slot, strict)
+        if meta["identity"]:
+            cols_v = None
+            wp = ops.pack_weight(p_w)
+        else:
+            wp = torch.zeros(out_ch, H * dv_slot, dtype=F32, device=a_kv.device)
+            cols_v = meta["rows_v"] - H * ops.HEAD_SLOT
+            wp[:, cols_v] = p_w.detach().reshape(out_ch, -1)
+            wp = ops.to_bf16(wp)
+        _, _, y = ops.linear_fwd(o, wp, p_b.detach(), want_bf16=False, want_f32=True)
+        ctx.save_for_backward(a_kv, q, kv, o, lse, wq, wkv, wp)
+        ctx.meta = dict(meta, n=n, h=h, w=w, cin=cin, ce=ce, cin_p=cin_p, H=H, embed=embed, out_ch=out_ch, strict=strict,
+                        cols_v=cols_v)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        a_kv, q, kv, o, lse, wq, wkv, wp = ctx.saved_tensors
+        m = ctx.meta
+        n, h, w, H, dv_slot = m["n"], m["h"], m["w"], m["H"], m["dv_slot"]
+        S = h * w
+        dev = dy.device
+        out_p = ops.round_up(m["out_ch"], 8)
+        dy = dy.contiguous()
+        if out_p == m["out_ch"]:
+            dy_b = torch.empty(dy.shape, dtype=BF16, device=dev)
+            L.act_cast(dy.float() if dy.dtype != F32 else dy, L.ACT_NONE, dy_b)
+        else:
+            dy_b = torch.zeros(dy.shape[0], out_p, dtype=BF16, device=dev)
+            dy_b[:, : m["out_ch"]] = dy
+        dp_b = ops.bias_grad(dy_b[:, : m["out_ch"]])
+        dwp = torch.zeros(out_p, H * dv_slot, dtype=F32, device=dev)
+        ops.linear_wgrad(dy_b, o, dwp)
+        do = ops.linear_dgrad(dy_b[:, : m["out_ch"]], wp)
+        k, v = kv[:, : H * ops.HEAD_SLOT], kv[:, H * ops.HEAD_SLOT:]
+        dq = torch.empty_like(q)
+        dkv = torch.empty_like(kv)
+        ops.attn_bwd(q, k, v, o, do, lse, dq, dkv[:, : H * ops.HEAD_SLOT], dkv[:, H * ops.HEAD_SLOT:], n, S, H, m["dk"],
+                     dv_slot, m["strict"])
+        dbq, dbkv = ops.bias_grad(dq), ops.bias_grad(dkv)
+        dwq = torch.zeros(wq.shape, dtype=F32, device=dev)
+        dwkv = torch.zeros(wkv.shape, dtype=F32, device=dev)
+        ops.linear_wgrad(dq, a_kv[:, : m["cin_p"]], dwq)
+        ops.linear_wgrad(dkv, a_kv, dwkv)
+        _, da_kv = ops.linear_dgrad(dkv, wkv, want_f32=True)
+        _, da_q = ops.linear_dgrad(dq, wq, want_f32=True)
+        da_kv[:, : m["cin"]] += da_q[:, : m["cin"]]
+        cin, ce, embed = m["cin"], m["ce"], m["embed"]
+        tail = (None,) * 7
+        if m["identity"]:
+            g_qw = dwq[:, :cin].reshape(embed, cin, 1, 1)
+            g_kvw = dwkv[:, : cin + ce].reshape(embed + m["out_ch"], cin + ce, 1, 1)
+            g_pw = dwp[: m["out_ch"]].reshape(m["out_ch"], m["out_ch"], 1, 1)
+            return (da_kv.to(BF16), g_qw, dbq, g_kvw, dbkv, g_pw, dp_b, *tail)
+        rq, rv = m["rows_q"], m["rows_v"]
+        g_qw = dwq[rq, :cin].reshape(embed, cin, 1, 1)
+        g_kvw = torch.cat((dwkv[rq, : cin + ce], dwkv[rv, : cin + ce])).reshape(embed + m["out_ch"], cin + ce, 1, 1)
+        g_pw = dwp[: m["out_ch"], m["cols_v"]].reshape(m["out_ch"], m["out_ch"], 1, 1)
+        return (da_kv.to(BF16), g_qw, dbq[rq], g_kvw, torch.cat((dbkv[rq], dbkv[rv])), g_pw, dp_b, *tail)
+
+
 class CausalAttention(nn.Module):
     """Autoregressively masked multi-head self-attention over image positions — API of reference
     nn/attention.py:66-161 (1x1-conv projections `_q`, `_kv`, `_proj`; heads are contiguous channel blocks;
@@ -328,6 +405,12 @@ class CausalAttention(nn.Module):
         self._kv = nn.Conv2d(in_channels=in_channels + extra_input_channels,
                              out_channels=self._embed_channels + self._out_channels, kernel_size=1)
         self._proj = nn.Conv2d(in_channels=self._out_channels, out_channels=self._out_channels, kernel_size=1)
+
+    def forward_pm(self, a_kv, geom, cin, ce):
+        """Pixel-major entry of the fused stacks: a_kv = [x (cin) | extra_x (ce) | 0-pad] bf16 -> fp32 [P, out]."""
+        return _AttentionPMFn.apply(a_kv, self._q.weight, self._q.bias, self._kv.weight, self._kv.bias, self._proj.weight,
+                                    self._proj.bias, self._n_heads, self._embed_channels, self._out_channels,
+                                    self._mask_center, geom, cin, ce)
 
     def forward(self, x, extra_x=None):
         _require_cuda(x, "CausalAttention")

@@ -20,6 +20,17 @@ from .. import ops
 F32, BF16 = torch.float32, torch.bfloat16
 
 
+SMALL_K = 160  # Cin*kh*kw at or below this goes to pg_conv_small_* (CUDA cores, fp32)
+
+
+def small_conv_ok(wshape):
+    """Shapes pg_conv_small_* handles: K = Cin*kh*kw <= 160 and the [K, Cout] fp32 weight tile of its dgrad kernel
+    within 200 KB of shared memory."""
+    cout, cin, kh, kw = wshape
+    k = cin * kh * kw
+    return k <= SMALL_K and k * cout * 4 <= 200 * 1024
+
+
 def conv_taps(kh, kw, pad_h, pad_w):
     """Offsets (dy, dx) of every kernel position, row-major like the OIHW weight."""
     return tuple((i - pad_h, j - pad_w) for i in range(kh) for j in range(kw))
@@ -86,6 +97,12 @@ def tap_conv2d(x, weight, bias, padding, pre_act=L.ACT_NONE, post_act=L.ACT_NONE
     kh, kw = weight.shape[-2:]
     if 2 * padding[0] < kh - 1 or 2 * padding[1] < kw - 1:
         raise NotImplementedError("tap_conv2d: padding too small for an input-sized output (not a shape on the path)")
+    if small_conv_ok(weight.shape) and post_act == L.ACT_NONE:
+        # a contraction this short (image-channel inputs, the 16/32-channel PixelCNN recipe) is not tensor-core work:
+        # direct fp32 kernel, exact to 1e-3 (no bf16 rounding of the operands)
+        from .modules import _SmallConvFn
+
+        return _SmallConvFn.apply(x, weight, bias, tuple(padding), pre_act)
     taps = conv_taps(kh, kw, padding[0], padding[1])
     if len(taps) > 32:
         raise NotImplementedError(f"tap_conv2d: {len(taps)} taps exceed the 32-tap gather (kernel {kh}x{kw})")

@@ -132,6 +132,47 @@ def linear_wgrad(dy, a, dw_out):
            split_k=_split_k_for(cout, cin, P), impl=GEMM_IMPL)
 
 
+# --------------------------------------------------------------------------------------------------
+# Tap-loop convolutions (im2col-free): the shifted operand is read in place through 4-D TMA boxes
+# --------------------------------------------------------------------------------------------------
+def conv_fwd(x, wcat, bias, n_img, h, w, taps, *, act=L.ACT_NONE, res0=None, res1=None, want_bf16=True, want_pre=False,
+             want_f32=False, pre_deriv=False):
+    """y[p] = bias + sum_t W_t . x[p + taps[t]] (zero outside the image).  x: [P, C] bf16 (C % 64 == 0),
+    wcat: [Cout, T*C] bf16 with tap-major columns.  Outputs as linear_fwd."""
+    P, C = x.shape
+    n = wcat.shape[0]
+    ob = empty((P, n), BF16, x) if want_bf16 else None
+    op = empty((P, n), BF16, x) if want_pre else None
+    of = empty((P, n), F32, x) if want_f32 else None
+    L.gemm_conv(x, wcat, P, n, len(taps) * C, L.CONV_FWD, n_img, h, w, C, taps, bias=bias, res0=res0, res1=res1,
+                out_bf16=ob, out_pre=op, out_f32=of, act=(act | L.ACT_STORE_DERIV) if (pre_deriv and want_pre) else act)
+    return ob, op, of
+
+
+def conv_dgrad(dy, wcat, cin, n_img, h, w, taps, *, aux=None, dact=L.ACT_NONE, want_f32=False, want_bf16=True, res0=None):
+    """dx[p] = sum_t W_t^T . dy[p - taps[t]] (optionally * act'(aux), + res0).  dy: [P, Cout] bf16 (Cout % 64 == 0),
+    wcat: [Cout, T*cin] bf16."""
+    P, cout = dy.shape
+    ob = empty((P, cin), BF16, dy) if want_bf16 else None
+    of = empty((P, cin), F32, dy) if want_f32 else None
+    L.gemm_conv(dy, wcat, P, cin, len(taps) * cout, L.CONV_DGRAD, n_img, h, w, cout, [(-a, -b) for a, b in taps], aux=aux,
+                dact=dact, res0=res0, out_bf16=ob, out_f32=of)
+    return ob, of
+
+
+def conv_wgrad(dy, x, dw_out, n_img, h, w, taps):
+    """dw_out[Cout, T*C] += sum_p dy[p]^T . x[p + taps[t]] (fp32 accumulation, split along pixels)."""
+    P, cout = dy.shape
+    C = x.shape[1]
+    T = len(taps)
+    assert dw_out.dtype == F32 and dw_out.shape[0] >= cout and dw_out.shape[1] == T * C
+    bn = 256 if C % 256 == 0 else (128 if C % 128 == 0 else 64)
+    tiles = ((cout + 127) // 128) * (T * C // bn)
+    k_iters = (P + 63) // 64
+    split = max(1, min(max(1, L.sm_count() // tiles), k_iters // 8 if k_iters >= 16 else 1))
+    L.gemm_conv(dy, x, cout, T * C, P, L.CONV_WGRAD, n_img, h, w, C, taps, out_f32=dw_out, accumulate=True, split_k=split)
+
+
 def bias_grad(dy, out=None):
     """Column sums of dy [P, C] into a fp32 [C] vector."""
     C = dy.shape[1]

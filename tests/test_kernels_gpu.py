@@ -453,6 +453,59 @@ def test_attention_fwd_bwd(L, case, impl):
 
 
 # --------------------------------------------------------------------------------------------------
+# Tap-loop convolution on the GEMM kernel (4-D TMA shifted boxes, no im2col buffer)
+# --------------------------------------------------------------------------------------------------
+def _shift(x, dy, dx):
+    """out[n, h, w] = x[n, h + dy, w + dx], zero outside the image (x: [N, H, W, C])."""
+    N, H, W, C = x.shape
+    out = torch.zeros_like(x)
+    h0, h1 = max(0, -dy), min(H, H - dy)
+    w0, w1 = max(0, -dx), min(W, W - dx)
+    if h1 > h0 and w1 > w0:
+        out[:, h0:h1, w0:w1] = x[:, h0 + dy:h1 + dy, w0 + dx:w1 + dx]
+    return out
+
+
+TAPS_3x3 = [(i - 1, j - 1) for i in range(3) for j in range(3)]
+CONV_GEMM_CASES = [
+    # N, H, W, Cin, Cout, taps
+    (4, 32, 32, 128, 256, [(0, -1), (0, 0), (0, 1)]),              # GatedPixelCNN 1x3 (vertical stack)
+    (2, 32, 32, 256, 512, [(-1, -1), (-1, 0), (0, -1), (0, 0)]),   # PixelSNAIL 2x2 -> 2C
+    (3, 16, 32, 64, 64, [(-2, 0), (-1, 0)]),                       # Nx1 after the front crop
+    (2, 32, 32, 128, 128, TAPS_3x3),                               # wide CausalConv2d (all taps, masked by the weights)
+    (40, 32, 32, 256, 256, [(-1, -1), (-1, 0), (0, -1), (0, 0)]),  # enough tiles for the 2-CTA kernel
+    (2, 8, 16, 64, 192, [(0, -3), (0, -2), (0, -1), (0, 0)]),      # narrow image (W = 16), 1x4 causal
+]
+
+
+@pytest.mark.parametrize("case", CONV_GEMM_CASES)
+def test_conv_gemm_fwd_dgrad_wgrad(L, case):
+    from pytorch_generative_b200 import ops
+
+    N, H, W, Cin, Cout, taps = case
+    T, P = len(taps), N * H * W
+    g = torch.Generator().manual_seed(21)
+    x = torch.randn(P, Cin, generator=g).to(_dev()).bfloat16()
+    wcat = (torch.randn(Cout, T * Cin, generator=g) / (T * Cin) ** 0.5).to(_dev()).bfloat16()
+    bias = torch.randn(Cout, generator=g).to(_dev())
+    dy = torch.randn(P, Cout, generator=g).to(_dev()).bfloat16()
+    # fp32 reference of the same tap sum
+    xr = x.float().view(N, H, W, Cin).requires_grad_(True)
+    wr = wcat.float().requires_grad_(True)
+    y_ref = bias + sum(_shift(xr, dy_, dx_).reshape(P, Cin) @ wr[:, t * Cin:(t + 1) * Cin].t() for t, (dy_, dx_) in enumerate(taps))
+    y_ref.backward(dy.float())
+    _, _, y = ops.conv_fwd(x, wcat, bias, N, H, W, taps, want_bf16=False, want_f32=True)
+    dxb, dxf = ops.conv_dgrad(dy, wcat, Cin, N, H, W, taps, want_f32=True)
+    dw = torch.zeros(Cout, T * Cin, device=_dev())
+    ops.conv_wgrad(dy, x, dw, N, H, W, taps)
+    torch.cuda.synchronize()
+    assert_close("conv gemm y", y, y_ref.detach(), rtol=1e-3, atol=1e-3)
+    assert_close("conv gemm dx", dxf, xr.grad.reshape(P, Cin), rtol=1e-3, atol=1e-3)
+    assert_close("conv gemm dx bf16", dxb, xr.grad.reshape(P, Cin), rtol=2 ** -7, atol=1e-2)
+    assert_close("conv gemm dw", dw, wr.grad, rtol=1e-3, atol=2e-3 * (P ** 0.5))
+
+
+# --------------------------------------------------------------------------------------------------
 # Small-Cin causal conv
 # --------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("N,Cin,H,W,Cout,k", [(4, 3, 32, 32, 512, 3), (3, 1, 28, 28, 32, 7), (2, 3, 8, 8, 24, 3),

@@ -270,6 +270,15 @@ def test_sampling_follows_reference_raster_order(pg, name):
     ("pixel_snail", "PixelSNAIL", dict(in_channels=3, out_channels=3, n_channels=64, n_pixel_snail_blocks=2,
                                        n_residual_blocks=2, attention_key_channels=16, attention_value_channels=32),
      (2, 3, 32, 32)),
+    # 64-channel variants: wide enough for the fused pixel-major stacks (TMA tap-loop convolutions, nn/pm.py)
+    ("gated_pixel_cnn", "GatedPixelCNN", dict(in_channels=3, out_channels=3, n_gated=3, gated_channels=64,
+                                              head_channels=32), (2, 3, 32, 32)),
+    ("gated_pixel_cnn", "GatedPixelCNN", dict(in_channels=1, out_channels=1, n_gated=2, gated_channels=64,
+                                              head_channels=16), (3, 1, 16, 32)),
+    # 28 x 28 images: no TMA tap loop (W does not divide 64) -> the module path with gathered taps
+    ("pixel_snail", "PixelSNAIL", dict(in_channels=1, out_channels=1, n_channels=64, n_pixel_snail_blocks=1,
+                                       n_residual_blocks=1, attention_key_channels=8, attention_value_channels=32),
+     (2, 1, 28, 28)),
 ])
 def test_conv_models_match_oracle(pg, name, cls, cfg, shape):
     """Mid-size PixelCNN / GatedPixelCNN / PixelSNAIL (tap-list convs on the tensor-core GEMM, wide channels) against
