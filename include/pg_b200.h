@@ -232,6 +232,17 @@ int pg_tap_scatter(const void* dxcat /* bf16 [P, T*C] */, int N, int H, int W, i
                    float* dx_f32, void* dx_bf16, int64_t ld_dx, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * LinearCausalAttention numerator — reference nn/attention.py:168-200 (`_UnnormalizedLinearCausalAttention`: a Python loop
+ * over the sequence, forward and backward).  q, k: [B, L, d] fp32, v / g / out: [B, L, dv] fp32, B = images x heads,
+ * contiguous.  out_i = q_i . S_i,  S_i = sum_{j <= i} k_j^T v_j.  Backward: dq_i = g_i S_i^T; with R_i = sum_{j >= i}
+ * q_j^T g_j: dv_i = k_i R_i, dk_i = v_i R_i^T.  One CTA per (image, head), state in registers, O(L (d + dv)) memory.
+ * d <= 64, dv <= 128.
+ * ------------------------------------------------------------------------------------------- */
+int pg_linear_attn_fwd(const float* q, const float* k, const float* v, float* out, int B, int L, int d, int dv, void* stream);
+int pg_linear_attn_bwd(const float* q, const float* k, const float* v, const float* g, float* dq, float* dk, float* dv_out,
+                       int B, int L, int d, int dv, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Optimizer part of the training step — reference trainer.py:182-191 (`clip_grad_norm_(model.parameters(), max_norm)`
  * then `optimizer.step()` with torch.optim.Adam as every recipe builds it, e.g. image_gpt.py:155) over ALL parameters in
  * two launches.  Tensors are given as device arrays of device pointers (one entry per parameter, fp32, contiguous);
@@ -244,11 +255,15 @@ int pg_tap_scatter(const void* dxcat /* bf16 [P, T*C] */, int N, int H, int W, i
  *                   g *= c (written back only when c < 1), m = b1 m + (1-b1) g, v = b2 v + (1-b2) g^2,
  *                   p -= lr / (1-b1^step) * m / (sqrt(v) / sqrt(1-b2^step) + eps)      (torch.optim.Adam, no amsgrad).
  * ------------------------------------------------------------------------------------------- */
+/* dst[t][i] = bf16(src[t][i]) for many fp32 tensors in one launch (same pointer-array / chunk-table convention): the
+ * per-step refresh of the bf16 tensor-core copies of the fp32 master weights. */
+int pg_cast_multi_bf16(const void* src_ptrs, const void* dst_ptrs, const int64_t* numel, const void* chunks, int n_chunks,
+                       int chunk_elems, void* stream);
 int pg_grad_sqnorm(const void* grad_ptrs, const int64_t* numel, const void* chunks, int n_chunks, int chunk_elems,
                    float* partials, void* stream);
 int pg_adam_step(const void* param_ptrs, const void* grad_ptrs, const void* exp_avg_ptrs, const void* exp_avg_sq_ptrs,
                  const int64_t* numel, const void* chunks, int n_chunks, int chunk_elems, const float* partials,
-                 float max_norm, float skip_above, float lr, float beta1, float beta2, float eps, int step,
+                 float max_norm, float skip_above, double lr, double beta1, double beta2, double eps, int step,
                  float* norm_out /* [2] */, void* stream);
 
 #ifdef __cplusplus

@@ -105,6 +105,32 @@ def causal_attention(x, p, prefix, n_heads, embed_channels, out_channels, mask_c
     return F.conv2d(out, p[prefix + "_proj.weight"], p[prefix + "_proj.bias"])
 
 
+def linear_causal_attention(x, p, prefix, n_heads, embed_channels, out_channels, feature_fn=None):
+    """LinearCausalAttention.forward — reference nn/attention.py:252-275 with the sequential numerator of
+    `_UnnormalizedLinearCausalAttention` (:168-180) written as the same running sum (autograd differentiates the loop; the
+    reference's hand-written backward :182-199 computes the same gradients).  The normaliser keeps the reference's
+    `K.cumsum(1)` over dimension 1 of the [N, heads, L, d] tensors."""
+    feature_fn = feature_fn or (lambda t: F.elu(t) + 1)
+    n, _, h, w = x.shape
+
+    def heads(t):
+        return t.view(n, n_heads, t.shape[1] // n_heads, -1).transpose(2, 3)
+
+    q = heads(F.conv2d(x, p[prefix + "_query.weight"], p[prefix + "_query.bias"]))
+    kv = F.conv2d(x, p[prefix + "_kv.weight"], p[prefix + "_kv.bias"])
+    k, v = kv.split([embed_channels, out_channels], dim=1)
+    k, v = heads(k), heads(v)
+    q, k = feature_fn(q), feature_fn(k)
+    den = 1 / (torch.einsum("nlhi,nlhi->nlh", q, k.cumsum(1)) + 1e-10)
+    rows, state = [], 0
+    for i in range(v.shape[2]):
+        state = state + k[:, :, i:i + 1].transpose(2, 3) @ v[:, :, i:i + 1]
+        rows.append(q[:, :, i:i + 1] @ state)
+    num = torch.cat(rows, dim=2)
+    out = num * den.unsqueeze(-1)
+    return out.transpose(2, 3).contiguous().view(n, -1, h, w)
+
+
 # --------------------------------------------------------------------------------------------------
 # Model stacks (state_dict keys are the reference's, SURVEY.md §8b)
 # --------------------------------------------------------------------------------------------------

@@ -16,7 +16,7 @@ CSRC = os.path.join(_HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 LIB_PATH = os.path.join(_HERE, "libpg_b200.so")
 
-SOURCES = ["pg_host.cu", "pg_gemm.cu", "pg_elementwise.cu", "pg_attention.cu", "pg_conv.cu", "pg_optim.cu"]
+SOURCES = ["pg_host.cu", "pg_gemm.cu", "pg_elementwise.cu", "pg_attention.cu", "pg_conv.cu", "pg_optim.cu", "pg_linear_attn.cu"]
 import glob
 
 HEADERS = sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + [os.path.join(INCLUDE, "pg_b200.h")]

@@ -71,8 +71,12 @@ _SIGNATURES = {
     "pg_conv_small_bwd": [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp],
     "pg_attn_decode": [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i32, _i32, _i32, _i32, _i32,
                        _f32, _i32, _vp],
+    "pg_linear_attn_fwd": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp],
+    "pg_linear_attn_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp],
+    "pg_cast_multi_bf16": [_vp, _vp, _vp, _vp, _i32, _i32, _vp],
     "pg_grad_sqnorm": [_vp, _vp, _vp, _i32, _i32, _vp, _vp],
-    "pg_adam_step": [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _f32, _f32, _f32, _f32, _f32, _f32, _i32, _vp, _vp],
+    "pg_adam_step": [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _f32, _f32, ctypes.c_double, ctypes.c_double,
+                     ctypes.c_double, ctypes.c_double, _i32, _vp, _vp],
     "pg_tap_gather": [_vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _vp],
     "pg_tap_scatter": [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _i64, _vp, _vp, _i64, _vp],
 }
@@ -420,6 +424,30 @@ def conv_small_bwd(x, w, dy_pm, pad, dw=None, dbias=None, dx=None, pre_act=ACT_N
     assert dy_pm.dtype == torch.float32 and dy_pm.is_contiguous()
     _check(lib.pg_conv_small_bwd(_ptr(x), _ptr(w), _ptr(dy_pm), N, Cin, H, W, Cout, kh, kw, pad[0], pad[1], pre_act,
                                  _ptr(dw), _ptr(dbias), _ptr(dx), _stream()), "pg_conv_small_bwd")
+
+
+@_device_guarded
+def linear_attn_fwd(q, k, v, out):
+    """q, k: [B, L, d]; v, out: [B, L, dv]; fp32 contiguous."""
+    B, Lq, d = q.shape
+    for t in (q, k, v, out):
+        assert t.dtype == torch.float32 and t.is_contiguous()
+    _check(load().pg_linear_attn_fwd(_ptr(q), _ptr(k), _ptr(v), _ptr(out), B, Lq, d, v.shape[2], _stream()), "pg_linear_attn_fwd")
+
+
+@_device_guarded
+def linear_attn_bwd(q, k, v, g, dq, dk, dv):
+    B, Lq, d = q.shape
+    for t in (q, k, v, g, dq, dk, dv):
+        assert t.dtype == torch.float32 and t.is_contiguous()
+    _check(load().pg_linear_attn_bwd(_ptr(q), _ptr(k), _ptr(v), _ptr(g), _ptr(dq), _ptr(dk), _ptr(dv), B, Lq, d, v.shape[2],
+                                     _stream()), "pg_linear_attn_bwd")
+
+
+@_device_guarded
+def cast_multi(src_ptrs, dst_ptrs, numel, chunks, n_chunks, chunk_elems):
+    _check(load().pg_cast_multi_bf16(_ptr(src_ptrs), _ptr(dst_ptrs), _ptr(numel), _ptr(chunks), n_chunks, chunk_elems,
+                                     _stream()), "pg_cast_multi_bf16")
 
 
 @_device_guarded

@@ -29,7 +29,9 @@ struct AttnArgs {
   float* dq_accum;
   int N, S, H, dk, dv, strict;
   float scale;
-  int dbg;  // PG_ATTN_DEBUG (timing experiments only): 1 = no MMAs issued, 2 = no softmax-thread arithmetic
+  int dbg;  // PG_ATTN_DEBUG (timing experiments only): 1 = no MMAs issued, 2 = no softmax-thread arithmetic,
+            // 3 = dQ drain without the TMA reduce, 4 = dQ drain reads TMEM only, 5 = no P / dS stores (and fences),
+            // 6 = no MUFU, 7 = no fence.proxy.async
 };
 
 // One warp per (image, head, query row).

@@ -15,8 +15,8 @@
 //   * the CTA is persistent: work items are dealt statically, balanced and L2-local (see Bwd2Cursor), K/V of the next item and
 //     Q / dO of the next tiles are prefetched through multi-stage rings, TMEM and barriers are set up once.
 //
-// Warp roles (448 threads): 0-3 softmax group A (key columns 0-63), 4-7 group B (64-127), thread = query row;
-// 8-11 dQ drain (thread = query row) + dV / dK read-out at the end of an item (thread = key row); 12 TMA producer; 13 TMEM owner + MMA issuer.
+// Warp roles (SW = 2: 448 threads, SW = 4: 704): 4 * SW softmax warps, group g = key columns [g * 128 / SW, ...), thread =
+// query row; then 4 warps of dQ drain (thread = query row) + dV / dK read-out at the end of an item (thread = key row); 12 TMA producer; 13 TMEM owner + MMA issuer.
 #pragma once
 
 namespace {
@@ -85,10 +85,17 @@ __device__ __forceinline__ bool bwd2_next(Bwd2Cursor& c, const AttnArgs& a, int 
   return true;
 }
 
-template <int DV>
-__global__ void __launch_bounds__(448, 1)
+// SW = softmax warpgroups: each covers 128 / SW key columns of every query row (2: 64 columns per thread, 448 threads;
+// 4: 32 columns per thread, 704 threads -- twice the warps per scheduler to hide the TMEM-load / fence / barrier latencies
+// of a stage, which is what bounds the 2-group kernel: profiles/r02_attn_bwd2_v2_ncu.txt).
+template <int DV, int SW>
+__global__ void __launch_bounds__(SW * 128 + 192, 1)
 attn_bwd2_kernel(const __grid_constant__ AttnTmaps tm, const AttnArgs a, const int T) {
   using C = Bwd2<DV>;
+  constexpr int CPT = 128 / SW;       // key columns per softmax thread
+  constexpr int NCH = CPT / 32;       // 32-column chunks per thread
+  constexpr int W_DRAIN = 4 * SW;     // first warp of the dQ drain group
+  constexpr int W_TMA = 4 * SW + 4, W_MMA = 4 * SW + 5;
   constexpr int V_BYTES = C::V_BYTES;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sK = smem + C::OFF_K;
@@ -128,13 +135,13 @@ attn_bwd2_kernel(const __grid_constant__ AttnTmaps tm, const AttnArgs a, const i
     }
     for (int s = 0; s < 3; ++s) { mbar_init(&q_full[s], 1); mbar_init(&q_empty[s], 1); }
     mbar_init(s_full, 1); mbar_init(dp_full, 1);
-    mbar_init(p_full, 8); mbar_init(ds_full, 8);  // one elected arrival per softmax warp
+    mbar_init(p_full, 4 * SW); mbar_init(ds_full, 4 * SW);  // one elected arrival per softmax warp
     mbar_init(p_free, 1); mbar_init(ds_free, 1);
     mbar_init(acc_full, 1); mbar_init(acc_empty, 4);
     fence_barrier_init();
     fence_proxy_async_smem();
   }
-  if (warp == 13) tmem_alloc<512>(tmem_slot);
+  if (warp == W_MMA) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -143,68 +150,74 @@ attn_bwd2_kernel(const __grid_constant__ AttnTmaps tm, const AttnArgs a, const i
   Bwd2Cursor c;
   bwd2_item(c, 0, a, T);
 
-  if (warp == 12) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+  if (warp == W_TMA) {
+    // ===================== TMA producer (whole warp converged, one elected lane issues) =====================
+    {
       unsigned g = 0, m = 0;
       while (c.valid) {
         if (c.it == 0) {
           const unsigned ks = m % C::NKV;
           mbar_wait(&kv_empty[ks], ((m / C::NKV) & 1u) ^ 1u);
-          mbar_arrive_expect_tx(&kv_full[ks], ATOM_BYTES + V_BYTES);
-          tma_load_3d(sK + ks * ATOM_BYTES, &tm.k, &kv_full[ks], c.h * 64, c.j * AT, c.n);
+          mbar_arrive_expect_tx_w(&kv_full[ks], ATOM_BYTES + V_BYTES);
+          tma_load_3d_w(sK + ks * ATOM_BYTES, &tm.k, &kv_full[ks], c.h * 64, c.j * AT, c.n);
 #pragma unroll
           for (int v = 0; v < DV / 64; ++v)
-            tma_load_3d(sV + ks * V_BYTES + v * ATOM_BYTES, &tm.v, &kv_full[ks], c.h * DV + v * 64, c.j * AT, c.n);
+            tma_load_3d_w(sV + ks * V_BYTES + v * ATOM_BYTES, &tm.v, &kv_full[ks], c.h * DV + v * 64, c.j * AT, c.n);
         }
         const int i = c.j + c.it;
         const unsigned qs = g % C::NQ, os = g % C::NDO;
         mbar_wait(&q_empty[qs], ((g / C::NQ) & 1u) ^ 1u);
-        mbar_arrive_expect_tx(&q_full[qs], ATOM_BYTES);
-        tma_load_3d(sQ + qs * ATOM_BYTES, &tm.q, &q_full[qs], c.h * 64, i * AT, c.n);
+        mbar_arrive_expect_tx_w(&q_full[qs], ATOM_BYTES);
+        tma_load_3d_w(sQ + qs * ATOM_BYTES, &tm.q, &q_full[qs], c.h * 64, i * AT, c.n);
         mbar_wait(&do_empty[os], ((g / C::NDO) & 1u) ^ 1u);
-        mbar_arrive_expect_tx(&do_full[os], V_BYTES);
+        mbar_arrive_expect_tx_w(&do_full[os], V_BYTES);
 #pragma unroll
         for (int v = 0; v < DV / 64; ++v)
-          tma_load_3d(sdO + os * V_BYTES + v * ATOM_BYTES, &tm.d_o, &do_full[os], c.h * DV + v * 64, i * AT, c.n);
+          tma_load_3d_w(sdO + os * V_BYTES + v * ATOM_BYTES, &tm.d_o, &do_full[os], c.h * DV + v * 64, i * AT, c.n);
         ++g;
         if (bwd2_next(c, a, T)) ++m;
       }
     }
-  } else if (warp == 13) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+  } else if (warp == W_MMA) {
+    // ===================== MMA issuer (whole warp converged, one elected lane issues: see umma_bf16_ss_w) =====================
+    {
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);   // S = Q K^T, dP = dO V^T
       constexpr uint32_t idesc_dv = umma_idesc_bf16(128, DV, 1, 1);   // dV += P^T dO
       constexpr uint32_t idesc_dk = umma_idesc_bf16(128, 64, 1, 1);   // dK += dS^T Q
       constexpr uint32_t idesc_dq = umma_idesc_bf16(128, 64, 0, 1);   // dQ  = dS K
-      const uint32_t p_addr = smem_u32(sP), ds_addr = smem_u32(sdS);
+      // descriptors: one base per operand tile, the K step only moves the 14-bit start-address field
+      //   K-major:  step kk -> atom kk / 4, 32 bytes per step inside the atom;   MN-major: 16 rows = 2048 bytes per step
+      auto kstep = [](uint64_t base, int kk) { return base + (uint64_t)((kk >> 2) * (ATOM_BYTES >> 4) + (kk & 3) * 2); };
+      auto mnstep = [](uint64_t base, int kk) { return base + (uint64_t)(kk * 128); };
+      const uint64_t p_mn = umma_desc_sw128(smem_u32(sP), ATOM_BYTES, 1024);
+      const uint64_t ds_mn = umma_desc_sw128(smem_u32(sdS), ATOM_BYTES, 1024);
+      const uint64_t ds_k = umma_desc_sw128(smem_u32(sdS), 16, 1024);
       auto k_of = [&](unsigned m) { return smem_u32(sK + (m % C::NKV) * ATOM_BYTES); };
       auto v_of = [&](unsigned m) { return smem_u32(sV + (m % C::NKV) * V_BYTES); };
       auto q_of = [&](unsigned g) { return smem_u32(sQ + (g % C::NQ) * ATOM_BYTES); };
       auto do_of = [&](unsigned g) { return smem_u32(sdO + (g % C::NDO) * V_BYTES); };
+      const bool mma_on = a.dbg != 1;
       auto issue_s = [&](unsigned g, unsigned m, bool first_of_item) {
         if (first_of_item) mbar_wait(&kv_full[m % C::NKV], (m / C::NKV) & 1u);
         mbar_wait(&q_full[g % C::NQ], (g / C::NQ) & 1u);
         tc_fence_after();
-        const uint32_t qa = q_of(g), ka = k_of(m);
-        if (a.dbg != 1)
+        const uint64_t qd = umma_desc_sw128(q_of(g), 16, 1024), kd = umma_desc_sw128(k_of(m), 16, 1024);
+        if (mma_on) {
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk)
-          umma_bf16_ss(tmem + C::COL_S, desc_kmajor(qa, kk), desc_kmajor(ka, kk), idesc_s, kk > 0);
-        umma_commit(s_full);
+          for (int kk = 0; kk < 4; ++kk) umma_bf16_ss_w(tmem + C::COL_S, kstep(qd, kk), kstep(kd, kk), idesc_s, kk > 0);
+        }
+        umma_commit_w(s_full);
       };
       auto issue_dp = [&](unsigned g, unsigned m) {
         mbar_wait(&do_full[g % C::NDO], (g / C::NDO) & 1u);
         tc_fence_after();
-        const uint32_t da = do_of(g), va = v_of(m);
-        if (a.dbg != 1)
+        const uint64_t dd = umma_desc_sw128(do_of(g), 16, 1024), vd = umma_desc_sw128(v_of(m), 16, 1024);
+        if (mma_on) {
 #pragma unroll
-        for (int kk = 0; kk < DV / 16; ++kk)
-          umma_bf16_ss(tmem + C::COL_DP, desc_kmajor(da, kk), desc_kmajor(va, kk), idesc_s, kk > 0);
-        umma_commit(dp_full);
+          for (int kk = 0; kk < DV / 16; ++kk) umma_bf16_ss_w(tmem + C::COL_DP, kstep(dd, kk), kstep(vd, kk), idesc_s, kk > 0);
+        }
+        umma_commit_w(dp_full);
       };
-      const bool mma_on = a.dbg != 1;
       unsigned g = 0, m = 0;
       if (c.valid) {
         issue_s(0, 0, true);
@@ -217,7 +230,8 @@ attn_bwd2_kernel(const __grid_constant__ AttnTmaps tm, const AttnArgs a, const i
         // with a single K/V stage the next item's operands cannot land before this item releases them
         const bool defer = (C::NKV == 1) && crosses;
         const bool first = c.it == 0, last = c.it == c.niter - 1;
-        const uint32_t qa = q_of(g), da = do_of(g), ka = k_of(m);
+        const uint64_t q_mn = umma_desc_sw128(q_of(g), ATOM_BYTES, 1024), do_mn = umma_desc_sw128(do_of(g), ATOM_BYTES, 1024);
+        const uint64_t k_mn = umma_desc_sw128(k_of(m), ATOM_BYTES, 1024);
 
         mbar_wait(p_full, g & 1u);  // P(g) published; S is free
         tc_fence_after();
@@ -226,33 +240,36 @@ attn_bwd2_kernel(const __grid_constant__ AttnTmaps tm, const AttnArgs a, const i
           mbar_wait(acc_empty, (m & 1u) ^ 1u);
           tc_fence_after();
         }
-        if (mma_on)
+        if (mma_on) {
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk)  // K = 128 queries
-          umma_bf16_ss(tmem + C::COL_DV, desc_mnmajor(p_addr, kk), desc_mnmajor(da, kk), idesc_dv, (!first || kk > 0));
-        umma_commit(p_free);
-        umma_commit(&do_empty[g % C::NDO]);
+          for (int kk = 0; kk < 8; ++kk)  // K = 128 queries
+            umma_bf16_ss_w(tmem + C::COL_DV, mnstep(p_mn, kk), mnstep(do_mn, kk), idesc_dv, (!first || kk > 0));
+        }
+        umma_commit_w(p_free);
+        umma_commit_w(&do_empty[g % C::NDO]);
 
         mbar_wait(ds_full, g & 1u);  // dS(g) published; dP is free
         tc_fence_after();
-        if (mma_on)
+        if (mma_on) {
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk)
-          umma_bf16_ss(tmem + C::COL_DK, desc_mnmajor(ds_addr, kk), desc_mnmajor(qa, kk), idesc_dk, (!first || kk > 0));
-        umma_commit(&q_empty[g % C::NQ]);
+          for (int kk = 0; kk < 8; ++kk)
+            umma_bf16_ss_w(tmem + C::COL_DK, mnstep(ds_mn, kk), mnstep(q_mn, kk), idesc_dk, (!first || kk > 0));
+        }
+        umma_commit_w(&q_empty[g % C::NQ]);
         if (nx.valid && !defer) issue_dp(g + 1, mn);
         const unsigned b = g % C::NDQ;
         mbar_wait(&dq_empty[b], ((g / C::NDQ) & 1u) ^ 1u);
         tc_fence_after();
-        if (mma_on)
+        if (mma_on) {
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk)  // K = 128 keys
-          umma_bf16_ss(tmem + C::COL_DQ + b * 64, desc_kmajor(ds_addr, kk), desc_mnmajor(ka, kk), idesc_dq, kk > 0);
-        umma_commit(&dq_full[b]);
-        umma_commit(ds_free);
+          for (int kk = 0; kk < 8; ++kk)  // K = 128 keys
+            umma_bf16_ss_w(tmem + C::COL_DQ + b * 64, kstep(ds_k, kk), mnstep(k_mn, kk), idesc_dq, kk > 0);
+        }
+        umma_commit_w(&dq_full[b]);
+        umma_commit_w(ds_free);
         if (last) {
-          umma_commit(acc_full);
-          umma_commit(&kv_empty[m % C::NKV]);
+          umma_commit_w(acc_full);
+          umma_commit_w(&kv_empty[m % C::NKV]);
         }
         if (nx.valid && defer) {
           issue_s(g + 1, mn, true);
@@ -263,38 +280,44 @@ attn_bwd2_kernel(const __grid_constant__ AttnTmaps tm, const AttnArgs a, const i
         ++g;
       }
     }
-  } else if (warp >= 8) {
+  } else if (warp >= W_DRAIN) {
     // ===================== dQ drain: TMEM -> fp32 slab -> TMA reduce-add =====================
     const int r = (warp & 3) * 32 + lane;
     const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
-    const bool leader = threadIdx.x == 256;
+    const bool leader = threadIdx.x == W_DRAIN * 32;
     unsigned g = 0, m = 0;
     while (c.valid) {
       const unsigned b = g % C::NDQ;
       const int i = c.j + c.it;
       mbar_wait(&dq_full[b], (g / C::NDQ) & 1u);
       tc_fence_after();
-      uint32_t v0[32], v1[32];
-      tmem_ld_32x32b_x32(tmem + C::COL_DQ + b * 64 + lane_base, v0);
-      tmem_ld_32x32b_x32(tmem + C::COL_DQ + b * 64 + lane_base + 32, v1);
-      tmem_wait_ld();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&dq_empty[b]);
+      if (a.dbg != 4) {
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        if (leader) tma_store_wait_read<0>();  // the previous reduce has finished reading the slab
-        __syncwarp();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (half == 0) slab32_store_scaled(sdQ, r, v0, a.scale);
-        else slab32_store_scaled(sdQ, r, v1, a.scale);
-        fence_proxy_async_smem();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (leader) {
-          tma_reduce_add_3d(&tm.dq, sdQ, c.h * 64 + half * 32, i * AT, c.n);
-          tma_store_commit();
+        for (int half = 0; half < 2; ++half) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tmem + C::COL_DQ + b * 64 + lane_base + half * 32, v);
+          tmem_wait_ld();
+          if (half == 1) {  // the accumulator has been copied out: the tensor core may overwrite it
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&dq_empty[b]);
+          }
+          if (leader) tma_store_wait_read<0>();  // the previous reduce has finished reading the slab
+          __syncwarp();
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          slab32_store_scaled(sdQ, r, v, a.scale);
+          fence_proxy_async_smem();
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (leader && a.dbg != 3) {
+            tma_reduce_add_3d(&tm.dq, sdQ, c.h * 64 + half * 32, i * AT, c.n);
+            tma_store_commit();
+          }
+          __syncwarp();
         }
+      } else {
+        tc_fence_before();
         __syncwarp();
+        if (lane == 0) mbar_arrive(&dq_empty[b]);
       }
       if (c.it == c.niter - 1) {
         // ---- dV_j, dK_j read-out (thread == key row): off the softmax threads, which move on to the next item ----
@@ -346,7 +369,7 @@ attn_bwd2_kernel(const __grid_constant__ AttnTmaps tm, const AttnArgs a, const i
     __syncwarp();
   } else {
     // ===================== softmax groups: thread == query row, group == key-column half =====================
-    const int grp = warp >> 2;              // 0: columns 0-63, 1: columns 64-127
+    const int grp = warp >> 2;              // key columns [grp * CPT, +CPT)
     const int r = (warp & 3) * 32 + lane;   // TMEM lane / tile row
     const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
     const float sl2 = a.scale * 1.4426950408889634f;
@@ -381,22 +404,26 @@ attn_bwd2_kernel(const __grid_constant__ AttnTmaps tm, const AttnArgs a, const i
       // ---- stage A: S -> P ----
       mbar_wait(s_full, g & 1u);
       tc_fence_after();
-      uint32_t pk[2][16];
+      uint32_t pk[NCH][16];
       const bool work = a.dbg != 2;
       if (work) {
-        uint32_t sv[2][32];
-        tmem_ld_32x32b_x32(tmem + C::COL_S + lane_base + (grp * 2) * 32, sv[0]);
-        tmem_ld_32x32b_x32(tmem + C::COL_S + lane_base + (grp * 2 + 1) * 32, sv[1]);
+        uint32_t sv[NCH][32];
+#pragma unroll
+        for (int cc = 0; cc < NCH; ++cc) tmem_ld_32x32b_x32(tmem + C::COL_S + lane_base + (grp * NCH + cc) * 32, sv[cc]);
         tmem_wait_ld();
         auto p_tile = [&](auto masked) {
           constexpr bool MASK = decltype(masked)::value;
 #pragma unroll
-          for (int cc = 0; cc < 2; ++cc) {
-            const int cb = k0 + (grp * 2 + cc) * 32;
+          for (int cc = 0; cc < NCH; ++cc) {
+            const int cb = k0 + (grp * NCH + cc) * 32;
 #pragma unroll
             for (int e = 0; e < 32; e += 2) {
-              float p0 = fast_exp2(fmaf(__uint_as_float(sv[cc][e]), sl2, -lse2));
-              float p1 = fast_exp2(fmaf(__uint_as_float(sv[cc][e + 1]), sl2, -lse2));
+              float p0 = fmaf(__uint_as_float(sv[cc][e]), sl2, -lse2);
+              float p1 = fmaf(__uint_as_float(sv[cc][e + 1]), sl2, -lse2);
+              if (a.dbg != 6) {
+                p0 = fast_exp2(p0);
+                p1 = fast_exp2(p1);
+              }
               if (MASK) {
                 if (cb + e > qlim) p0 = 0.f;
                 if (cb + e + 1 > qlim) p1 = 0.f;
@@ -409,11 +436,11 @@ attn_bwd2_kernel(const __grid_constant__ AttnTmaps tm, const AttnArgs a, const i
         else p_tile(std::false_type{});
       }
       if (g > 0) mbar_wait(p_free, (g - 1) & 1u);  // dV(g-1) no longer reads sP
-      if (work) {
-        store_tile_row_chunk(sP, r, grp * 2, pk[0]);
-        store_tile_row_chunk(sP, r, grp * 2 + 1, pk[1]);
+      if (work && a.dbg != 5) {
+#pragma unroll
+        for (int cc = 0; cc < NCH; ++cc) store_tile_row_chunk(sP, r, grp * NCH + cc, pk[cc]);
       }
-      fence_proxy_async_smem();
+      if (a.dbg != 7 && a.dbg != 5) fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();  // one arrival per warp: every arrival wakes the warps parked on this SM's barriers
       if (lane == 0) mbar_arrive(p_full);
@@ -422,12 +449,12 @@ attn_bwd2_kernel(const __grid_constant__ AttnTmaps tm, const AttnArgs a, const i
       mbar_wait(dp_full, g & 1u);
       tc_fence_after();
       if (work) {
-        uint32_t dv[2][32];
-        tmem_ld_32x32b_x32(tmem + C::COL_DP + lane_base + (grp * 2) * 32, dv[0]);
-        tmem_ld_32x32b_x32(tmem + C::COL_DP + lane_base + (grp * 2 + 1) * 32, dv[1]);
+        uint32_t dv[NCH][32];
+#pragma unroll
+        for (int cc = 0; cc < NCH; ++cc) tmem_ld_32x32b_x32(tmem + C::COL_DP + lane_base + (grp * NCH + cc) * 32, dv[cc]);
         tmem_wait_ld();
 #pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
+        for (int cc = 0; cc < NCH; ++cc) {
 #pragma unroll
           for (int e = 0; e < 32; e += 2) {
             const float2 p = unpack_bf16x2(pk[cc][e >> 1]);
@@ -438,11 +465,11 @@ attn_bwd2_kernel(const __grid_constant__ AttnTmaps tm, const AttnArgs a, const i
         }
       }
       if (g > 0) mbar_wait(ds_free, (g - 1) & 1u);  // dK(g-1), dQ(g-1) no longer read sdS
-      if (work) {
-        store_tile_row_chunk(sdS, r, grp * 2, pk[0]);
-        store_tile_row_chunk(sdS, r, grp * 2 + 1, pk[1]);
+      if (work && a.dbg != 5) {
+#pragma unroll
+        for (int cc = 0; cc < NCH; ++cc) store_tile_row_chunk(sdS, r, grp * NCH + cc, pk[cc]);
       }
-      fence_proxy_async_smem();
+      if (a.dbg != 7 && a.dbg != 5) fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(ds_full);
@@ -453,7 +480,7 @@ attn_bwd2_kernel(const __grid_constant__ AttnTmaps tm, const AttnArgs a, const i
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 13) {
+  if (warp == W_MMA) {
     tc_fence_after();
     tmem_dealloc<512>(tmem);
   }
@@ -480,12 +507,16 @@ int attn_bwd_tc2(const AttnArgs& a, cudaStream_t stream) {
   if (groups > a.N * a.H) groups = a.N * a.H;
   if (groups < 1) groups = 1;
   const unsigned grid = (unsigned)(groups * slots);
+  static const int sw = getenv("PG_ATTN_BWD_SW") ? atoi(getenv("PG_ATTN_BWD_SW")) : 4;
+  auto launch = [&](auto kern, int smem, int threads) -> int {
+    PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    kern<<<grid, threads, smem, stream>>>(tm, a, T);
+    return 0;
+  };
   if (a.dv == 64) {
-    PG_CUDA(cudaFuncSetAttribute(attn_bwd2_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, Bwd2<64>::SMEM));
-    attn_bwd2_kernel<64><<<grid, 448, Bwd2<64>::SMEM, stream>>>(tm, a, T);
+    if (sw == 2 ? launch(attn_bwd2_kernel<64, 2>, Bwd2<64>::SMEM, 448) : launch(attn_bwd2_kernel<64, 4>, Bwd2<64>::SMEM, 704)) return 1;
   } else {
-    PG_CUDA(cudaFuncSetAttribute(attn_bwd2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, Bwd2<128>::SMEM));
-    attn_bwd2_kernel<128><<<grid, 448, Bwd2<128>::SMEM, stream>>>(tm, a, T);
+    if (sw == 2 ? launch(attn_bwd2_kernel<128, 2>, Bwd2<128>::SMEM, 448) : launch(attn_bwd2_kernel<128, 4>, Bwd2<128>::SMEM, 704)) return 1;
   }
   if (pg_check_launch("pg_causal_attn_bwd(tcgen05, pipelined)")) return 1;
   const long long P = (long long)a.N * a.S;

@@ -131,31 +131,35 @@ attn_fwd_tc_kernel(const __grid_constant__ AttnTmaps tm, const AttnArgs a, const
   const uint32_t tmem_s = tmem, tmem_o = tmem + 128;
 
   if (warp == 4) {
-    if (lane == 0) {
-      mbar_arrive_expect_tx(q_full, ATOM_BYTES);
-      tma_load_3d(sQ, &tm.q, q_full, h * 64, i * AT, n);
+    {  // TMA producer: whole warp converged, one elected lane issues (see umma_bf16_ss_w)
+      mbar_arrive_expect_tx_w(q_full, ATOM_BYTES);
+      tma_load_3d_w(sQ, &tm.q, q_full, h * 64, i * AT, n);
       for (int j = 0; j < ntiles; ++j) {
         const int st = j & 1;
         mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
-        mbar_arrive_expect_tx(&kv_full[st], ATOM_BYTES + V_BYTES);
-        tma_load_3d(sK + st * ATOM_BYTES, &tm.k, &kv_full[st], h * 64, j * AT, n);
+        mbar_arrive_expect_tx_w(&kv_full[st], ATOM_BYTES + V_BYTES);
+        tma_load_3d_w(sK + st * ATOM_BYTES, &tm.k, &kv_full[st], h * 64, j * AT, n);
 #pragma unroll
         for (int v = 0; v < DV / 64; ++v)
-          tma_load_3d(sV + st * V_BYTES + v * ATOM_BYTES, &tm.v, &kv_full[st], h * DV + v * 64, j * AT, n);
+          tma_load_3d_w(sV + st * V_BYTES + v * ATOM_BYTES, &tm.v, &kv_full[st], h * DV + v * 64, j * AT, n);
       }
     }
   } else if (warp == 5) {
-    if (lane == 0) {
+    {  // MMA issuer: whole warp converged
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
       constexpr uint32_t idesc_o = umma_idesc_bf16(128, DV, 0, 1);
-      const uint32_t q_addr = smem_u32(sQ), p_addr = smem_u32(sP);
+      auto kstep = [](uint64_t base, int kk) { return base + (uint64_t)((kk >> 2) * (ATOM_BYTES >> 4) + (kk & 3) * 2); };
+      auto mnstep = [](uint64_t base, int kk) { return base + (uint64_t)(kk * 128); };
+      const uint64_t q_d = umma_desc_sw128(smem_u32(sQ), 16, 1024), p_d = umma_desc_sw128(smem_u32(sP), 16, 1024);
       mbar_wait(q_full, 0);
       mbar_wait(&kv_full[0], 0);
       tc_fence_after();
+      {
+        const uint64_t k_d = umma_desc_sw128(smem_u32(sK), 16, 1024);
 #pragma unroll
-      for (int kk = 0; kk < 4; ++kk)
-        umma_bf16_ss(tmem_s, desc_kmajor(q_addr, kk), desc_kmajor(smem_u32(sK), kk), idesc_s, kk > 0);
-      umma_commit(s_full);
+        for (int kk = 0; kk < 4; ++kk) umma_bf16_ss_w(tmem_s, kstep(q_d, kk), kstep(k_d, kk), idesc_s, kk > 0);
+      }
+      umma_commit_w(s_full);
       for (int j = 0; j < ntiles; ++j) {
         const int st = j & 1;
         mbar_wait(p_full, j & 1);  // P(j) in smem; every softmax thread is done reading S(j)
@@ -164,18 +168,16 @@ attn_fwd_tc_kernel(const __grid_constant__ AttnTmaps tm, const AttnArgs a, const
           const int sn = (j + 1) & 1;
           mbar_wait(&kv_full[sn], ((j + 1) >> 1) & 1);
           tc_fence_after();
-          const uint32_t k_addr = smem_u32(sK + sn * ATOM_BYTES);
+          const uint64_t k_d = umma_desc_sw128(smem_u32(sK + sn * ATOM_BYTES), 16, 1024);
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk)
-            umma_bf16_ss(tmem_s, desc_kmajor(q_addr, kk), desc_kmajor(k_addr, kk), idesc_s, kk > 0);
-          umma_commit(s_full);
+          for (int kk = 0; kk < 4; ++kk) umma_bf16_ss_w(tmem_s, kstep(q_d, kk), kstep(k_d, kk), idesc_s, kk > 0);
+          umma_commit_w(s_full);
         }
-        const uint32_t v_addr = smem_u32(sV + st * V_BYTES);
+        const uint64_t v_d = umma_desc_sw128(smem_u32(sV + st * V_BYTES), ATOM_BYTES, 1024);
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk)
-          umma_bf16_ss(tmem_o + st * DV, desc_kmajor(p_addr, kk), desc_mnmajor(v_addr, kk), idesc_o, kk > 0);
-        umma_commit(o_full);
-        umma_commit(&kv_empty[st]);
+        for (int kk = 0; kk < 8; ++kk) umma_bf16_ss_w(tmem_o + st * DV, kstep(p_d, kk), mnstep(v_d, kk), idesc_o, kk > 0);
+        umma_commit_w(o_full);
+        umma_commit_w(&kv_empty[st]);
       }
     }
   } else {

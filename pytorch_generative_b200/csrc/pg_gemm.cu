@@ -282,8 +282,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int num_tiles = p.num_m_blk * p.num_n_blk * p.splits;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ===================== TMA producer =====================
+    {
+      // ===================== TMA producer (whole warp converged, one elected lane issues) =====================
       int s = 0;
       uint32_t ph = 0;
       for (int tile = tile_first; tile < num_tiles; tile += tile_stride) {
@@ -299,76 +299,76 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           uint8_t* sB = sA + A_STAGE_BYTES;
           if (TWO) {
             // both CTAs load their halves; all bytes are accounted on the leader's barrier
-            if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * STAGE_BYTES);
+            if (rank == 0) mbar_arrive_expect_tx_w(&full_bar[s], 2 * STAGE_BYTES);
             const int row0 = m_blk * MT + rank * BM, nb0 = n_blk * BN + rank * B_ROWS;
             int bcol = nb0, brow = kit * BK;  // MN-major B coordinates
             if (p.conv.mode == 1) {
               const int t = kit / p.conv.cslabs, cs = kit - t * p.conv.cslabs;
               const int hw = p.conv.H * p.conv.W, n = row0 / hw, h0 = (row0 - n * hw) / p.conv.W;
-              tma_load_4d_2sm(sA, &tmA, &full_bar[s], cs * 64, p.conv.dx[t], h0 + p.conv.dy[t], n);
+              tma_load_4d_2sm_w(sA, &tmA, &full_bar[s], cs * 64, p.conv.dx[t], h0 + p.conv.dy[t], n);
               bcol = t * p.N + nb0;  // dgrad: W^T of tap t starts at column t * Cin of the packed weight
               brow = cs * 64;
             } else {
-              tma_load_2d_2sm(sA, &tmA, &full_bar[s], kit * BK, row0);
+              tma_load_2d_2sm_w(sA, &tmA, &full_bar[s], kit * BK, row0);
             }
             if (!B_MN) {
-              tma_load_2d_2sm(sB, &tmB, &full_bar[s], kit * BK, nb0);
+              tma_load_2d_2sm_w(sB, &tmB, &full_bar[s], kit * BK, nb0);
             } else {
 #pragma unroll
               for (int j = 0; j < B_ROWS / 64; ++j)
-                tma_load_2d_2sm(sB + j * (BK * 128), &tmB, &full_bar[s], bcol + j * 64, brow);
+                tma_load_2d_2sm_w(sB + j * (BK * 128), &tmB, &full_bar[s], bcol + j * 64, brow);
             }
             if (++s == STAGES) { s = 0; ph ^= 1; }
             continue;
           }
-          mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+          mbar_arrive_expect_tx_w(&full_bar[s], STAGE_BYTES);
           if (p.conv.mode != 0) {
             const int hw = p.conv.H * p.conv.W;
             if (p.conv.mode == 1) {  // A = activations under tap t (forward / dgrad)
               const int t = kit / p.conv.cslabs, cs = kit - t * p.conv.cslabs;
               const int row0 = m_blk * BM, n = row0 / hw, h0 = (row0 - n * hw) / p.conv.W;
-              tma_load_4d(sA, &tmA, &full_bar[s], cs * 64, p.conv.dx[t], h0 + p.conv.dy[t], n);
+              tma_load_4d_w(sA, &tmA, &full_bar[s], cs * 64, p.conv.dx[t], h0 + p.conv.dy[t], n);
               if (!B_MN) {
-                tma_load_2d(sB, &tmB, &full_bar[s], kit * BK, n_blk * BN);
+                tma_load_2d_w(sB, &tmB, &full_bar[s], kit * BK, n_blk * BN);
               } else {
 #pragma unroll
                 for (int j = 0; j < BN / 64; ++j)
-                  tma_load_2d(sB + j * (BK * 128), &tmB, &full_bar[s], t * p.N + n_blk * BN + j * 64, cs * 64);
+                  tma_load_2d_w(sB + j * (BK * 128), &tmB, &full_bar[s], t * p.N + n_blk * BN + j * 64, cs * 64);
               }
             } else {  // wgrad: A = dY (MN-major), B = activations under the tap this N block belongs to
               const int t = n_blk / p.conv.nbpt, nb = n_blk - t * p.conv.nbpt;
               const int pix0 = kit * BK, n = pix0 / hw, h0 = (pix0 - n * hw) / p.conv.W;
 #pragma unroll
               for (int j = 0; j < BM / 64; ++j)
-                tma_load_2d(sA + j * (BK * 128), &tmA, &full_bar[s], m_blk * BM + j * 64, kit * BK);
+                tma_load_2d_w(sA + j * (BK * 128), &tmA, &full_bar[s], m_blk * BM + j * 64, kit * BK);
 #pragma unroll
               for (int j = 0; j < BN / 64; ++j)
-                tma_load_4d(sB + j * (BK * 128), &tmB, &full_bar[s], nb * BN + j * 64, p.conv.dx[t], h0 + p.conv.dy[t], n);
+                tma_load_4d_w(sB + j * (BK * 128), &tmB, &full_bar[s], nb * BN + j * 64, p.conv.dx[t], h0 + p.conv.dy[t], n);
             }
             if (++s == STAGES) { s = 0; ph ^= 1; }
             continue;
           }
           if (!A_MN) {
-            tma_load_2d(sA, &tmA, &full_bar[s], kit * BK, m_blk * BM);  // box {64 k, 128 rows}
+            tma_load_2d_w(sA, &tmA, &full_bar[s], kit * BK, m_blk * BM);  // box {64 k, 128 rows}
           } else {
 #pragma unroll
             for (int j = 0; j < BM / 64; ++j)  // box {64 m, 64 k-rows} per 64-wide MN atom
-              tma_load_2d(sA + j * (BK * 128), &tmA, &full_bar[s], m_blk * BM + j * 64, kit * BK);
+              tma_load_2d_w(sA + j * (BK * 128), &tmA, &full_bar[s], m_blk * BM + j * 64, kit * BK);
           }
           if (!B_MN) {
-            tma_load_2d(sB, &tmB, &full_bar[s], kit * BK, n_blk * BN);
+            tma_load_2d_w(sB, &tmB, &full_bar[s], kit * BK, n_blk * BN);
           } else {
 #pragma unroll
             for (int j = 0; j < BN / 64; ++j)
-              tma_load_2d(sB + j * (BK * 128), &tmB, &full_bar[s], n_blk * BN + j * 64, kit * BK);
+              tma_load_2d_w(sB + j * (BK * 128), &tmB, &full_bar[s], n_blk * BN + j * 64, kit * BK);
           }
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && rank == 0) {
-      // ===================== MMA issuer (leader CTA only when paired) =====================
+    if (rank == 0) {
+      // ===================== MMA issuer (leader CTA only when paired; whole warp converged, elected lane issues) =====================
       constexpr uint32_t idesc = umma_idesc_bf16(MT, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
       int s = 0;
       uint32_t ph = 0;
@@ -387,25 +387,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
           const uint32_t b_addr = a_addr + A_STAGE_BYTES;
+          // one descriptor per operand stage; a K step (16 elements) only moves the start-address field:
+          // K-major: 32 bytes inside the swizzle span; MN-major: 16 k-rows of 128 B = 2048 bytes (LBO = atom stride)
+          const uint64_t a_base = A_MN ? umma_desc_sw128(a_addr, BK * 128, 1024) : umma_desc_sw128(a_addr, 16, 1024);
+          const uint64_t b_base = B_MN ? umma_desc_sw128(b_addr, BK * 128, 1024) : umma_desc_sw128(b_addr, 16, 1024);
 #pragma unroll
           for (int kk = 0; kk < BK / 16; ++kk) {
-            // K-major: 16 elements = 32 bytes inside the swizzle span; rows are 128B apart, 8-row groups 1024B.
-            // MN-major: 16 k-rows of 128B = 2048 bytes; 64-wide MN atoms are BK*128 bytes apart (LBO).
-            const uint64_t a_desc = A_MN ? umma_desc_sw128(a_addr + kk * 2048, BK * 128, 1024)
-                                         : umma_desc_sw128(a_addr + kk * 32, 16, 1024);
-            const uint64_t b_desc = B_MN ? umma_desc_sw128(b_addr + kk * 2048, BK * 128, 1024)
-                                         : umma_desc_sw128(b_addr + kk * 32, 16, 1024);
-            if (TWO) umma_bf16_ss_2sm(d_tmem, a_desc, b_desc, idesc, (kit > k0 || kk > 0) ? 1u : 0u);
-            else umma_bf16_ss(d_tmem, a_desc, b_desc, idesc, (kit > k0 || kk > 0) ? 1u : 0u);
+            const uint64_t a_desc = a_base + (uint64_t)(A_MN ? kk * 128 : kk * 2);
+            const uint64_t b_desc = b_base + (uint64_t)(B_MN ? kk * 128 : kk * 2);
+            if (TWO) umma_bf16_ss_2sm_w(d_tmem, a_desc, b_desc, idesc, (kit > k0 || kk > 0) ? 1u : 0u);
+            else umma_bf16_ss_w(d_tmem, a_desc, b_desc, idesc, (kit > k0 || kk > 0) ? 1u : 0u);
           }
           // frees the smem stage (in both CTAs when paired) once these MMAs have read it
-          if (TWO) umma_commit_2sm(&empty_bar[s]);
-          else umma_commit(&empty_bar[s]);
+          if (TWO) umma_commit_2sm_w(&empty_bar[s]);
+          else umma_commit_w(&empty_bar[s]);
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
         // accumulator complete -> epilogue(s)
-        if (TWO) umma_commit_2sm(&tfull_bar[as]);
-        else umma_commit(&tfull_bar[as]);
+        if (TWO) umma_commit_2sm_w(&tfull_bar[as]);
+        else umma_commit_w(&tfull_bar[as]);
         if (++as == ACC_STAGES) { as = 0; aph ^= 1; }
       }
     }

@@ -58,6 +58,29 @@ grad_sqnorm_kernel(const float* const* __restrict__ grads, const int64_t* __rest
   if (threadIdx.x == 0) partials[blockIdx.x] = s;
 }
 
+// fp32 -> bf16 copies of many tensors in one launch (the per-step refresh of the tensor-core weight operands)
+__global__ void __launch_bounds__(OPT_THREADS)
+cast_multi_kernel(const float* const* __restrict__ src, bf16* const* __restrict__ dst, const int64_t* __restrict__ numel,
+                  const int2* __restrict__ chunks, int chunk_elems) {
+  const int2 ck = chunks[blockIdx.x];
+  const float* x = src[ck.x];
+  bf16* y = dst[ck.x];
+  const int64_t n = numel[ck.x];
+  const int64_t lo = (int64_t)ck.y * chunk_elems;
+  const int64_t hi = min(lo + (int64_t)chunk_elems, n);
+  int64_t tail = lo;
+  if (((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0) {
+    const int64_t lo8 = lo / 8, hi8 = hi / 8;
+    for (int64_t i = lo8 + threadIdx.x; i < hi8; i += OPT_THREADS) {
+      const float4 a = reinterpret_cast<const float4*>(x)[2 * i], b = reinterpret_cast<const float4*>(x)[2 * i + 1];
+      reinterpret_cast<uint4*>(y)[i] =
+          make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w));
+    }
+    tail = hi8 * 8;
+  }
+  for (int64_t i = tail + threadIdx.x; i < hi; i += OPT_THREADS) y[i] = __float2bfloat16(x[i]);
+}
+
 struct AdamArgs {
   float* const* params;
   float* const* grads;
@@ -68,14 +91,14 @@ struct AdamArgs {
   const float* partials;
   int n_chunks, chunk_elems;
   float max_norm, skip_above;  // skip_above <= 0: never skip
-  float lr_over_bc1, rsqrt_bc2, beta1, beta2, eps;
+  float lr_over_bc1, rsqrt_bc2, beta1, beta2, omb1, omb2, eps;  // omb = 1 - beta, rounded from double like torch's scalars
   float* norm_out;  // [2]: total gradient norm, 1 if the update was applied else 0
 };
 
 __device__ __forceinline__ void adam_elem(float& p, float& g, float& m, float& v, const AdamArgs& a, float coef) {
   g *= coef;
-  m = a.beta1 * m + (1.f - a.beta1) * g;      // exp_avg.lerp_(grad, 1 - beta1)
-  v = a.beta2 * v + (1.f - a.beta2) * g * g;  // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value = 1 - beta2)
+  m = m + a.omb1 * (g - m);            // exp_avg.lerp_(grad, 1 - beta1)
+  v = a.beta2 * v + a.omb2 * (g * g);  // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value = 1 - beta2)
   const float denom = sqrtf(v) * a.rsqrt_bc2 + a.eps;
   p -= a.lr_over_bc1 * (m / denom);
 }
@@ -145,8 +168,9 @@ extern "C" int pg_grad_sqnorm(const void* grad_ptrs, const int64_t* numel, const
 
 extern "C" int pg_adam_step(const void* param_ptrs, const void* grad_ptrs, const void* exp_avg_ptrs, const void* exp_avg_sq_ptrs,
                             const int64_t* numel, const void* chunks, int n_chunks, int chunk_elems, const float* partials,
-                            float max_norm, float skip_above, float lr, float beta1, float beta2, float eps, int step,
+                            float max_norm, float skip_above, double lr, double beta1d, double beta2d, double epsd, int step,
                             float* norm_out, void* stream_) {
+  const float beta1 = (float)beta1d, beta2 = (float)beta2d, eps = (float)epsd;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   PG_REQUIRE(param_ptrs && grad_ptrs && exp_avg_ptrs && exp_avg_sq_ptrs && numel && chunks && partials && norm_out,
              "pg_adam_step: null argument");
@@ -164,12 +188,25 @@ extern "C" int pg_adam_step(const void* param_ptrs, const void* grad_ptrs, const
   a.max_norm = max_norm;
   a.skip_above = skip_above;
   // host-side scalars in double, like torch's _single_tensor_adam
-  const double bc1 = 1.0 - pow((double)beta1, (double)step);
-  const double bc2 = 1.0 - pow((double)beta2, (double)step);
-  a.lr_over_bc1 = (float)((double)lr / bc1);
+  const double bc1 = 1.0 - pow(beta1d, (double)step);
+  const double bc2 = 1.0 - pow(beta2d, (double)step);
+  a.lr_over_bc1 = (float)(lr / bc1);
   a.rsqrt_bc2 = (float)(1.0 / sqrt(bc2));
   a.beta1 = beta1; a.beta2 = beta2; a.eps = eps;
+  a.omb1 = (float)(1.0 - (double)beta1d);
+  a.omb2 = (float)(1.0 - (double)beta2d);
   a.norm_out = norm_out;
   adam_step_kernel<<<n_chunks, OPT_THREADS, 0, stream>>>(a);
   return pg_check_launch("pg_adam_step");
+}
+
+extern "C" int pg_cast_multi_bf16(const void* src_ptrs, const void* dst_ptrs, const int64_t* numel, const void* chunks,
+                                  int n_chunks, int chunk_elems, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  PG_REQUIRE(src_ptrs && dst_ptrs && numel && chunks && n_chunks > 0, "pg_cast_multi_bf16: null/empty argument");
+  PG_REQUIRE(chunk_elems > 0 && chunk_elems % 8 == 0, "pg_cast_multi_bf16: chunk_elems must be a positive multiple of 8");
+  cast_multi_kernel<<<n_chunks, OPT_THREADS, 0, stream>>>(reinterpret_cast<const float* const*>(src_ptrs),
+                                                         reinterpret_cast<bf16* const*>(dst_ptrs), numel,
+                                                         reinterpret_cast<const int2*>(chunks), chunk_elems);
+  return pg_check_launch("pg_cast_multi_bf16");
 }

@@ -41,6 +41,15 @@ class TransformerBlock(nn.Module):
             nn.Conv2d(in_channels=4 * n_channels, out_channels=n_channels, kernel_size=1),
         )
 
+    def forward(self, x):
+        """Standalone use of one block on an NCHW tensor (reference image_gpt.py:50-52), composed of the drop-in
+        modules; `ImageGPT.forward` does not come through here (it runs the fused stack)."""
+        from ..nn.tapconv import tap_conv2d
+
+        h = x + self._attn(self._ln1(x))
+        t = tap_conv2d(self._ln2(h), self._out[0].weight, self._out[0].bias, (0, 0), post_act=L.ACT_GELU)
+        return h + tap_conv2d(t, self._out[2].weight, self._out[2].bias, (0, 0))
+
     def flat_params(self):
         a = self._attn
         return [self._ln1.weight, self._ln1.bias, a._q.weight, a._q.bias, a._kv.weight, a._kv.bias, a._proj.weight,
@@ -52,14 +61,15 @@ class _ImageGPTStack(torch.autograd.Function):
     """forward(x_nchw, params...) -> logits_nchw; one node for the whole network."""
 
     @staticmethod
-    def forward(ctx, x, n_heads, eps, *params):
+    def forward(ctx, x, n_heads, eps, packed, opts, *params):
         pos, in_w, in_b = params[0], params[1], params[2]
         n_blocks = (len(params) - 7) // PARAMS_PER_BLOCK
         ln_w, ln_b, out_w, out_b = params[-4:]
         n, cin, h, w = x.shape
         S, P, H = h * w, n * h * w, n_heads
         C = in_w.shape[0]
-        keep = any(ctx.needs_input_grad)
+        # needs_input_grad ignores torch.no_grad(): eval / sampling must not retain every block's activations
+        keep = any(ctx.needs_input_grad) and opts["grad"]
 
         x_in = (x + pos[:, :, : h, : w]).contiguous()  # sampling evaluates the top rows of the canvas only
         xs = torch.empty(P, C, dtype=F32, device=x.device)
@@ -69,25 +79,17 @@ class _ImageGPTStack(torch.autograd.Function):
         for b in range(n_blocks):
             (ln1_w, ln1_b, q_w, q_b, kv_w, kv_b, p_w, p_b, ln2_w, ln2_b, f1_w, f1_b, f2_w,
              f2_b) = params[3 + b * PARAMS_PER_BLOCK: 3 + (b + 1) * PARAMS_PER_BLOCK]
-            wq, bq, wkv, bkv, meta = pack_qkv_weights(q_w, q_b, kv_w, kv_b, H, C, C, C, C)
-            wqkv = torch.cat((wq, wkv))
-            bqkv = torch.cat((bq, bkv))
+            pk = packed["blocks"][b]
+            wqkv, bqkv, meta = pk["wqkv"], pk["bqkv"], pk["meta"]
             dv_slot, slot = meta["dv_slot"], ops.HEAD_SLOT
             a1, _, mean1, rstd1 = ops.layernorm_fwd(xs, ln1_w.detach(), ln1_b.detach(), eps)
             qkv, _, _ = ops.linear_fwd(a1, wqkv, bqkv)
             q, k, v = qkv[:, : H * slot], qkv[:, H * slot: 2 * H * slot], qkv[:, 2 * H * slot:]
             o, lse = ops.attn_fwd(q, k, v, n, S, H, meta["dk"], dv_slot, False)
-            cols_v = None
-            if meta["identity"]:
-                wp = ops.pack_weight(p_w)
-            else:
-                cols_v = meta["rows_v"] - H * slot
-                wp32 = torch.zeros(C, H * dv_slot, dtype=F32, device=x.device)
-                wp32[:, cols_v] = p_w.detach().reshape(C, -1)
-                wp = ops.to_bf16(wp32)
+            wp, cols_v = pk["wp"], pk["cols_v"]
             _, _, hres = ops.linear_fwd(o, wp, p_b.detach(), res0=xs, want_bf16=False, want_f32=True)
             a2, _, mean2, rstd2 = ops.layernorm_fwd(hres, ln2_w.detach(), ln2_b.detach(), eps)
-            w1, w2 = ops.pack_weight(f1_w), ops.pack_weight(f2_w)
+            w1, w2 = pk["w1"], pk["w2"]
             g, u, _ = ops.linear_fwd(a2, w1, f1_b.detach(), act=L.ACT_GELU, want_pre=True, pre_deriv=True)  # u = GELU'(pre)
             _, _, xs_new = ops.linear_fwd(g, w2, f2_b.detach(), res0=xs, res1=hres, want_bf16=False, want_f32=True)
             if keep:
@@ -96,16 +98,19 @@ class _ImageGPTStack(torch.autograd.Function):
             xs = xs_new
         af, _, mean_f, rstd_f = ops.layernorm_fwd(xs, ln_w.detach(), ln_b.detach(), eps)
         cout = out_w.shape[0]
-        wo = ops.pack_weight(out_w)
+        wo = packed["wo"]
         _, _, logits_pm = ops.linear_fwd(af, wo, out_b.detach(), want_bf16=False, want_f32=True)
         if keep:
             ctx.saved = dict(blocks=saved, x_in=x_in, xs_final=xs, af=af, mean_f=mean_f, rstd_f=rstd_f, wo=wo,
-                             params=params, dims=(n, cin, h, w, C, H, cout), eps=eps)
+                             params=params, dims=(n, cin, h, w, C, H, cout), eps=eps, hook=opts.get("hook"))
         return ops.pm_to_nchw(logits_pm, n, cout, h, w)
 
     @staticmethod
     def backward(ctx, dlogits):
-        sv = ctx.saved
+        sv = getattr(ctx, "saved", None)
+        if sv is None:
+            raise RuntimeError("ImageGPT: the activations of this forward were already consumed by a backward pass "
+                               "(retain_graph is not supported by the fused stack)")
         params = sv["params"]
         n, cin, h, w, C, H, cout = sv["dims"]
         S, P = h * w, n * h * w
@@ -141,7 +146,7 @@ class _ImageGPTStack(torch.autograd.Function):
 
         # data parallelism: each block's slice of the arena is handed to the bucket hook (an asynchronous all-reduce)
         # as soon as its last wgrad GEMM is queued; see parallel.OverlappedGradAverager
-        bucket_hook = _ImageGPTStack.grad_bucket_hook if _arena_views_are_grads(sv) else None
+        bucket_hook = sv["hook"] if _arena_views_are_grads(sv) else None
         pending = []
 
         for b in reversed(range(n_blocks)):
@@ -213,7 +218,7 @@ class _ImageGPTStack(torch.autograd.Function):
         ctx.saved = None
         for handle in pending:  # the gradients leave this node averaged
             handle.wait()
-        return (dx_in if ctx.needs_input_grad[0] else None, None, None, *grads)
+        return (dx_in if ctx.needs_input_grad[0] else None, None, None, None, None, *grads)
 
 
 def _arena_views_are_grads(sv):
@@ -222,7 +227,6 @@ def _arena_views_are_grads(sv):
     return bool(sv["blocks"]) and all(blk["meta"]["identity"] for blk in sv["blocks"])
 
 
-_ImageGPTStack.grad_bucket_hook = None  # set through ImageGPT.set_grad_bucket_hook (process-wide: one model per rank)
 
 
 class ImageGPT(base.AutoregressiveModel):
@@ -243,6 +247,83 @@ class ImageGPT(base.AutoregressiveModel):
         self._n_heads = n_attention_heads
         if n_embedding_channels % 8 != 0:
             raise NotImplementedError("ImageGPT: n_embedding_channels must be a multiple of 8 on the B200 path")
+
+    # ------------------------------------------------------------------------------------------------------------
+    # bf16 tensor-core copies of the weight matrices.  The fp32 Parameters stay the master weights (reference
+    # semantics: the optimizer updates them in place); the copies are rebuilt only when a parameter's version counter
+    # has moved (once per optimizer step; never between the forwards of eval / sampling), by ONE multi-tensor cast
+    # launch into a fresh bf16 arena (q | kv weights land adjacent, so the fused qkv projection needs no torch.cat) and
+    # one concatenation of all the q / kv biases.  A fresh arena per refresh: a backward that is still pending keeps
+    # reading the copies its forward used.
+    # ------------------------------------------------------------------------------------------------------------
+    def _packed_training_weights(self):
+        C, H = self._input.weight.shape[0], self._n_heads
+        blocks = list(self._transformer)
+        mats = [w for blk in blocks for w in (blk._attn._q.weight, blk._attn._kv.weight, blk._attn._proj.weight,
+                                              blk._out[0].weight, blk._out[2].weight)] + [self._out.weight]
+        biases = [b for blk in blocks for b in (blk._attn._q.bias, blk._attn._kv.bias)]
+        sig = (mats[0].data_ptr(), tuple(p._version for p in mats), tuple(p._version for p in biases))
+        cache = self.__dict__.setdefault("_wcache", {})
+        if cache.get("sig") == sig:
+            return cache["packed"]
+        dev = mats[0].device
+        cout = self._out.weight.shape[0]
+        identity = C // H == ops.HEAD_SLOT and C % 8 == 0
+        packed = {"blocks": []}
+        if identity and blocks:
+            per_block = 12 * C * C
+            arena = torch.empty(len(blocks) * per_block + cout * C, dtype=BF16, device=dev)
+            views, dsts = [], []
+            for b in range(len(blocks)):
+                base = b * per_block
+                wqkv = arena[base: base + 3 * C * C].view(3 * C, C)
+                wp = arena[base + 3 * C * C: base + 4 * C * C].view(C, C)
+                w1 = arena[base + 4 * C * C: base + 8 * C * C].view(4 * C, C)
+                w2 = arena[base + 8 * C * C: base + 12 * C * C].view(C, 4 * C)
+                views.append((wqkv, wp, w1, w2))
+                dsts += [wqkv[:C], wqkv[C:], wp, w1, w2]
+            wo = arena[len(blocks) * per_block:].view(cout, C)
+            dsts.append(wo)
+            plan = cache.get("plan")
+            if plan is None or plan["src_key"] != tuple(p.data_ptr() for p in mats):
+                from .. import optim
+
+                numel = [p.numel() for p in mats]
+                chunks = [(t, c) for t, n in enumerate(numel) for c in range((n + optim.CHUNK - 1) // optim.CHUNK)]
+                plan = dict(src_key=tuple(p.data_ptr() for p in mats), n_chunks=len(chunks), chunk=optim.CHUNK,
+                            numel=torch.tensor(numel, dtype=torch.int64, device=dev),
+                            chunks=torch.tensor(chunks, dtype=torch.int32, device=dev).contiguous(),
+                            src=torch.tensor([p.data_ptr() for p in mats], dtype=torch.int64, device=dev),
+                            host_dst=torch.empty(len(mats), dtype=torch.int64).pin_memory(),
+                            dst=torch.empty(len(mats), dtype=torch.int64, device=dev))
+                cache["plan"] = plan
+            for i, d in enumerate(dsts):
+                plan["host_dst"][i] = d.data_ptr()
+            plan["dst"].copy_(plan["host_dst"], non_blocking=True)
+            L.cast_multi(plan["src"], plan["dst"], plan["numel"], plan["chunks"], plan["n_chunks"], plan["chunk"])
+            ball = torch.cat([b.detach() for b in biases])  # [blocks * 3C]: q | kv biases of every block
+            meta = dict(dk=ops.HEAD_SLOT, dv=ops.HEAD_SLOT, dv_slot=ops.HEAD_SLOT, rows_q=None, rows_v=None, identity=True)
+            for b, (wqkv, wp, w1, w2) in enumerate(views):
+                packed["blocks"].append(dict(wqkv=wqkv, bqkv=ball[b * 3 * C: (b + 1) * 3 * C], wp=wp, w1=w1, w2=w2, meta=meta,
+                                             cols_v=None))
+            packed["wo"], packed["arena"] = wo, arena
+        else:  # narrow heads live in zero-padded 64-wide slots: scatter-pack per block
+            for blk in blocks:
+                a = blk._attn
+                wq, bq, wkv, bkv, meta = pack_qkv_weights(a._q.weight, a._q.bias, a._kv.weight, a._kv.bias, H, C, C, C, C)
+                if meta["identity"]:
+                    wp, cols_v = ops.pack_weight(a._proj.weight), None
+                else:
+                    cols_v = meta["rows_v"] - H * ops.HEAD_SLOT
+                    wp32 = torch.zeros(C, H * meta["dv_slot"], dtype=F32, device=dev)
+                    wp32[:, cols_v] = a._proj.weight.detach().reshape(C, -1)
+                    wp = ops.to_bf16(wp32)
+                packed["blocks"].append(dict(wqkv=torch.cat((wq, wkv)), bqkv=torch.cat((bq, bkv)), wp=wp,
+                                             w1=ops.pack_weight(blk._out[0].weight), w2=ops.pack_weight(blk._out[2].weight),
+                                             meta=meta, cols_v=cols_v))
+            packed["wo"] = ops.pack_weight(self._out.weight)
+        cache["sig"], cache["packed"] = sig, packed
+        return packed
 
     # ------------------------------------------------------------------------------------------------------------
     # Incremental sampling.  The reference's sample() (models/base.py:97-120) runs a full forward per pixel; the model is
@@ -365,7 +446,7 @@ class ImageGPT(base.AutoregressiveModel):
     # ---- data-parallel bucket protocol (parallel.OverlappedGradAverager) ----
     def set_grad_bucket_hook(self, fn):
         """fn(flat_fp32_bucket) -> handle with wait(); called once per transformer block during backward."""
-        _ImageGPTStack.grad_bucket_hook = fn
+        self.__dict__["_grad_bucket_hook"] = fn  # per model instance; None removes it
 
     def bucketed_parameters(self):
         """Parameters whose gradients are averaged by the bucket hook (the block weight matrices), or [] when the
@@ -387,7 +468,8 @@ class ImageGPT(base.AutoregressiveModel):
         for blk in self._transformer:
             flat.extend(blk.flat_params())
         flat.extend([self._ln.weight, self._ln.bias, self._out.weight, self._out.bias])
-        return _ImageGPTStack.apply(x.float(), self._n_heads, self._ln.eps, *flat)
+        return _ImageGPTStack.apply(x.float(), self._n_heads, self._ln.eps, self._packed_training_weights(),
+                                    dict(grad=torch.is_grad_enabled(), hook=self.__dict__.get("_grad_bucket_hook")), *flat)
 
 
 def reproduce(*args, **kwargs):

@@ -422,3 +422,71 @@ class CausalAttention(nn.Module):
 def attention_scale(embed_channels, n_heads):
     """1/sqrt(dk) with dk = embed_channels / n_heads (reference nn/attention.py:152)."""
     return 1.0 / math.sqrt(embed_channels // n_heads)
+
+
+# --------------------------------------------------------------------------------------------------
+# LinearCausalAttention
+# --------------------------------------------------------------------------------------------------
+class _LinearAttnNumerator(torch.autograd.Function):
+    """Unnormalised causal linear attention (reference nn/attention.py:168-200): out_i = Q_i . sum_{j<=i} K_j^T V_j.
+    Q, K: [N, heads, L, d]; V: [N, heads, L, dv].  One kernel per direction instead of a Python loop over L."""
+
+    @staticmethod
+    def forward(ctx, Q, K, V):
+        n, h, l, d = Q.shape
+        q, k, v = (t.contiguous().float().view(n * h, l, -1) for t in (Q, K, V))
+        out = torch.empty_like(v)
+        L.linear_attn_fwd(q, k, v, out)
+        ctx.save_for_backward(q, k, v)
+        ctx.shape = (n, h, l)
+        return out.view(n, h, l, -1)
+
+    @staticmethod
+    def backward(ctx, G):
+        q, k, v = ctx.saved_tensors
+        n, h, l = ctx.shape
+        g = G.contiguous().float().view(n * h, l, -1)
+        dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+        L.linear_attn_bwd(q, k, v, g, dq, dk, dv)
+        return dq.view(n, h, l, -1), dk.view(n, h, l, -1), dv.view(n, h, l, -1)
+
+
+def _elu_plus_one(x):
+    return torch.nn.functional.elu(x) + 1
+
+
+class LinearCausalAttention(nn.Module):
+    """O(N)-memory causal attention with a kernel feature map — API of reference nn/attention.py:209-275 (`_query`, `_kv`
+    1x1-conv projections; `feature_fn` defaults to elu(x) + 1).
+
+    The arithmetic follows the reference line by line, including its normaliser
+    `1 / (einsum("nlhi,nlhi->nlh", Q, K.cumsum(1)) + 1e-10)`, whose cumulative sum runs over dimension 1 of the
+    [N, heads, L, d] tensors (the heads).  The sequential part — the running K^T V state — is one CUDA kernel per
+    direction (`pg_linear_attn_fwd/bwd`) instead of the reference's per-position Python loop."""
+
+    def __init__(self, in_channels, feature_fn=_elu_plus_one, n_heads=1, embed_channels=None, out_channels=None):
+        super().__init__()
+        self._feature_fn = feature_fn
+        self._n_heads = n_heads
+        self._embed_channels = embed_channels or in_channels
+        self._out_channels = out_channels or in_channels
+        self._query = nn.Conv2d(in_channels=in_channels, out_channels=self._embed_channels, kernel_size=1)
+        self._kv = nn.Conv2d(in_channels=in_channels, out_channels=self._embed_channels + self._out_channels, kernel_size=1)
+        self._numerator = _LinearAttnNumerator.apply
+
+    def forward(self, x):
+        _require_cuda(x, "LinearCausalAttention")
+        from .tapconv import tap_conv2d
+
+        n, _, h, w = x.shape
+
+        def to_multihead(t):  # (N, C, H, W) -> (N, heads, H*W, head_size)
+            return t.view(n, self._n_heads, t.shape[1] // self._n_heads, -1).transpose(2, 3)
+
+        q = to_multihead(tap_conv2d(x, self._query.weight, self._query.bias, (0, 0)))
+        k, v = tap_conv2d(x, self._kv.weight, self._kv.bias, (0, 0)).split([self._embed_channels, self._out_channels], dim=1)
+        k, v = to_multihead(k), to_multihead(v)
+        q, k = self._feature_fn(q), self._feature_fn(k)
+        den = 1 / (torch.einsum("nlhi,nlhi->nlh", q, k.cumsum(1)) + 1e-10)
+        out = self._numerator(q, k, v) * torch.unsqueeze(den, -1)
+        return out.transpose(2, 3).contiguous().view(n, -1, h, w)

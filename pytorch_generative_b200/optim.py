@@ -55,6 +55,7 @@ class FusedAdam(torch.optim.Optimizer):
         if len(self.param_groups) != 1:
             # the recipes use one group; several groups would each need the global norm first
             raise NotImplementedError("FusedAdam.clip_and_step supports a single parameter group")
+        self._opt_called = True  # what lr_scheduler's wrapper of step() records (its "step() before optimizer.step()" check)
         group = self.param_groups[0]
         params = [p for p in group["params"] if p.grad is not None]
         if not params:
@@ -83,6 +84,9 @@ class FusedAdam(torch.optim.Optimizer):
         L.adam_step(dp[0], dp[1], dp[2], dp[3], plan["numel"], plan["chunks"], plan["n_chunks"], CHUNK, plan["partials"],
                     float(min(max_norm, 3.0e38)), float(skip_above or 0.0), float(group["lr"]), beta1, beta2, group["eps"],
                     step, plan["norm_out"])
+        # the kernel wrote the parameters (and, when clipping, the gradients) through raw pointers: tell autograd and
+        # every version-keyed cache (the models' bf16 weight copies) that they changed
+        torch.autograd.graph.increment_version(params)
         norm = plan["norm_out"][0]
         applied = True
         if skip_above:

@@ -9,7 +9,8 @@ option; rebinding is.  `reproduce()` of each recipe constructs its model as `mod
 
 import importlib
 
-_NN_NAMES = ("CausalConv2d", "GatedActivation", "NCHWLayerNorm", "CausalAttention", "image_positional_encoding")
+_NN_NAMES = ("CausalConv2d", "GatedActivation", "NCHWLayerNorm", "CausalAttention", "LinearCausalAttention",
+             "image_positional_encoding")
 _MODEL_NAMES = {"PixelCNN": "pixel_cnn", "GatedPixelCNN": "gated_pixel_cnn", "PixelSNAIL": "pixel_snail",
                 "ImageGPT": "image_gpt"}
 _saved = {}

@@ -97,6 +97,7 @@ class OverlappedGradAverager:
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         params = list(model.parameters()) if params is None else list(params)
         bucketed = []
+        self._model = model
         if self.world > 1 and hasattr(model, "set_grad_bucket_hook"):
             model.set_grad_bucket_hook(bucket_all_reduce_mean)
             bucketed = list(model.bucketed_parameters())
@@ -107,6 +108,11 @@ class OverlappedGradAverager:
     def average_(self):
         """Call after backward: the arena-backed gradients were averaged inside backward already."""
         self.rest.average_()
+
+    def close(self):
+        """Detaches the bucket hook from the model (its backward then issues no collective any more)."""
+        if self.n_bucketed and hasattr(self._model, "set_grad_bucket_hook"):
+            self._model.set_grad_bucket_hook(None)
 
 
 def shard_seed(base_seed, rank):

@@ -14,6 +14,7 @@ Fixtures
   nn_blocks.pt    : CausalConv2d (3x3 A/B, 7x7 A, rectangular 3x5), GatedActivation (tanh / identity),
                     NCHWLayerNorm, CausalAttention (strict / non-strict, extra input, multi-head):
                     outputs and all gradients.
+  nn_linear_attention.pt : LinearCausalAttention (one head; two heads with embed != out channels): output, all gradients.
   receptive_fields.pt : debug.compute_receptive_field-style 7x7 causality patterns of the four models.
 """
 
@@ -178,6 +179,23 @@ def make_receptive_fields(pg):
     return out
 
 
+def make_linear_attention_fixture(pg):
+    """LinearCausalAttention (reference nn/attention.py:209-275): two head geometries, outputs and all gradients."""
+    out = {}
+    for tag, kwargs, shape in [("one_head", dict(in_channels=8), (2, 8, 5, 6)),
+                               ("two_heads", dict(in_channels=6, n_heads=2, embed_channels=8, out_channels=12), (2, 6, 4, 7))]:
+        torch.manual_seed(11)
+        m = pg.nn.LinearCausalAttention(**kwargs)
+        g = torch.Generator().manual_seed(12)
+        x = torch.randn(shape, generator=g).requires_grad_(True)
+        y = m(x)
+        dy = torch.randn(y.shape, generator=g)
+        y.backward(dy)
+        out[tag] = dict(kwargs=kwargs, state={k: v.detach().clone() for k, v in m.state_dict().items()}, x=x.detach().clone(),
+                        y=y.detach().clone(), dy=dy, grads=dict(x=x.grad.clone(), **{k: p.grad.clone() for k, p in m.named_parameters()}))
+    return out
+
+
 def main():
     if not os.path.isdir(REF):
         sys.exit("make_golden.py needs the reference checkout at /root/reference")
@@ -193,6 +211,8 @@ def main():
     torch.save(make_nn_fixture(pg), os.path.join(HERE, "nn_blocks.pt"))
     torch.save(make_receptive_fields(pg), os.path.join(HERE, "receptive_fields.pt"))
     print("nn_blocks.pt, receptive_fields.pt written")
+    torch.save(make_linear_attention_fixture(pg), os.path.join(HERE, "nn_linear_attention.pt"))
+    print("nn_linear_attention.pt written")
 
 
 if __name__ == "__main__":

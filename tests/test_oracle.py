@@ -189,3 +189,22 @@ def test_oracle_bitwise_causality_probe():
         x2[:, :, r + 1:, :] = -1
         out = O.forward(model, O.trainable(fx["state_before"]), x2, fx["cfg"]).detach()
         assert torch.equal(out[:, :, r, c], base[:, :, r, c]), model
+
+
+def test_linear_causal_attention_matches_reference_fixture():
+    """The oracle's LinearCausalAttention against outputs / gradients of the reference itself (nn/attention.py:209-275)."""
+    from oracle import reference_path as O
+
+    fx = torch.load(os.path.join(GOLD, "nn_linear_attention.pt"), weights_only=False)
+    for tag, f in fx.items():
+        kw = f["kwargs"]
+        embed = kw.get("embed_channels") or kw["in_channels"]
+        outc = kw.get("out_channels") or kw["in_channels"]
+        pt = O.trainable(f["state"])
+        x = f["x"].clone().requires_grad_(True)
+        y = O.linear_causal_attention(x, pt, "", kw.get("n_heads", 1), embed, outc)
+        y.backward(f["dy"])
+        assert torch.allclose(y, f["y"], rtol=1e-5, atol=1e-5), tag
+        assert torch.allclose(x.grad, f["grads"]["x"], rtol=1e-4, atol=1e-5), tag
+        for k, v in pt.items():
+            assert torch.allclose(v.grad, f["grads"][k], rtol=1e-4, atol=1e-4), (tag, k)

@@ -276,7 +276,7 @@ def test_trainer_follows_the_reference_step_and_checkpoint_format(tmp_path):
     tr2.restore_checkpoint()
     assert tr2._step == 3 and tr2._epoch == 1
     for (k, a), (_, b) in zip(tr.model.state_dict().items(), tr2.model.state_dict().items()):
-        assert torch.equal(a, b), k
+        assert torch.equal(a.cpu(), b.cpu()), k
     for pa, pb in zip(tr.model.parameters(), tr2.model.parameters()):
         assert torch.equal(opt.state[pa]["exp_avg"], opt2.state[pb]["exp_avg"])
     assert abs(opt2.param_groups[0]["lr"] - opt.param_groups[0]["lr"]) < 1e-12

@@ -119,6 +119,45 @@ def test_causal_attention_matches_reference(pg, tag):
         check(tag + " first pixel", y[:, :, 0, 0], m._proj.bias.detach().expand(y.shape[0], -1), 2e-3)
 
 
+@pytest.mark.parametrize("tag", ["one_head", "two_heads"])
+def test_linear_causal_attention_matches_reference(pg, tag):
+    """LinearCausalAttention (reference nn/attention.py:209-275) against the reference's own outputs and gradients: the
+    1x1 projections run on the fp32 direct kernel at these channel counts, the sequential numerator on pg_linear_attn_*."""
+    f = load("nn_linear_attention.pt")[tag]
+    m = pg.nn.LinearCausalAttention(**f["kwargs"]).to(dev())
+    m.load_state_dict(f["state"])
+    x = f["x"].to(dev()).requires_grad_(True)
+    y = m(x)
+    y.backward(f["dy"].to(dev()))
+    check(tag + " y", y, f["y"], TOL_F32)
+    check(tag + " dx", x.grad, f["grads"]["x"], TOL_F32)
+    for name, p in m.named_parameters():
+        check(f"{tag} d{name}", p.grad, f["grads"][name], TOL_F32)
+
+
+def test_linear_causal_attention_long_sequence_matches_oracle(pg):
+    """32 x 32 pixels, 4 heads of 16 -> 32 channels: the scan kernels across many staging blocks, against the oracle."""
+    from oracle import reference_path as O
+
+    torch.manual_seed(2)
+    m = pg.nn.LinearCausalAttention(in_channels=16, n_heads=4, embed_channels=64, out_channels=128)
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 16, 32, 32, generator=g) * 0.5
+    dy = torch.randn(2, 128, 32, 32, generator=g)
+    pt = O.trainable({k: v.detach().clone() for k, v in m.state_dict().items()})
+    xr = x.clone().requires_grad_(True)
+    yr = O.linear_causal_attention(xr, pt, "", 4, 64, 128)
+    yr.backward(dy)
+    m = m.to(dev())
+    xd = x.to(dev()).requires_grad_(True)
+    y = m(xd)
+    y.backward(dy.to(dev()))
+    check("linear attn y", y, yr, TOL_F32)
+    check("linear attn dx", xd.grad, xr.grad, TOL_F32)
+    for name, p in m.named_parameters():
+        check("linear attn d" + name, p.grad, pt[name].grad, TOL_F32)
+
+
 def test_positional_encoding_bit_identical(pg):
     f = load("nn_blocks.pt")["posenc"]
     assert torch.equal(pg.nn.image_positional_encoding(f["shape"]), f["value"])
