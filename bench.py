@@ -33,7 +33,7 @@ CONFIGS = {
     "c5": dict(name="ImageGPT 3x32x32 CIFAR-10-shaped, 24 blocks / 8 heads / 512 ch", cls="ImageGPT", oracle="image_gpt",
                cfg=dict(in_channels=3, out_channels=3, in_size=32, n_transformer_blocks=24, n_attention_heads=8,
                         n_embedding_channels=512),
-               shape=(3, 32, 32), batch=64, lr=5e-3, algo_gflop_per_img=541.289, cpu_batch=1),
+               shape=(3, 32, 32), batch=64, lr=5e-3, algo_gflop_per_img=541.289, cpu_batch=2),
     # BASELINE.json configs[1]
     "c2": dict(name="ImageGPT 1x28x28 MNIST-shaped, 8 blocks / 4 heads / 64 ch", cls="ImageGPT", oracle="image_gpt",
                cfg=dict(in_channels=1, out_channels=1, in_size=28, n_transformer_blocks=8, n_attention_heads=4,
@@ -82,10 +82,11 @@ def peaks():
 
 def measured_traffic():
     """DRAM bytes per GEMM launch from the committed ncu capture (None when the profile is absent)."""
-    path = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
-    if not os.path.exists(path):
-        return None
-    return round(json.load(open(path))["traffic_bytes_per_launch"])
+    for name in ("r02_gemm_traffic.json", "r01_gemm_traffic.json"):
+        path = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(path):
+            return round(json.load(open(path))["traffic_bytes_per_launch"])
+    return None
 
 
 class ClockSampler:
@@ -165,6 +166,7 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        parallel.configure_nccl()  # few NCCL CTAs: the gradient buckets need a fraction of NVLink, the GEMMs need the SMs
         with _stdout_to_stderr():  # NCCL prints its version banner on stdout; stdout carries the one JSON line only
             dist.init_process_group("nccl", device_id=dev)
             dist.barrier()
@@ -296,7 +298,8 @@ def run_ours(args):
         "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (pg_gemm_bf16, tcgen05 1x1-conv fwd/dgrad/wgrad)",
                      "achieved": round(achieved_tf, 1), "peak": pk["tf_sustained"], "unit": "TFLOP/s",
                      "frac": round(achieved_tf / pk["tf_sustained"], 4), "traffic": measured_traffic(),
-                     "traffic_unit": "DRAM bytes per launch (ncu dram__bytes_read+write, profiles/r01_gemm_traffic.json)",
+                     "traffic_unit": "DRAM bytes per launch (ncu dram__bytes_read+write over the 291 GEMMs of one step, "
+                                     "profiles/r02_gemm_traffic.json)",
                      "algo_bytes_per_launch": round(gemm_bytes / max(n_gemm, 1)),
                      "flops_per_launch": round(gemm_flops / max(n_gemm, 1)),
                      "launches_timed": n_gemm, "share_of_step": round(gemm_ms / ms_instr, 4),
@@ -322,31 +325,47 @@ def run_ours(args):
 # --------------------------------------------------------------------------------------------------
 # Reference arm / cpu_baseline: the oracle port of the reference's CPU path on the host cores
 # --------------------------------------------------------------------------------------------------
-def _oracle_state(spec):
-    """Reference-default init of the same architecture.  Built from our Module (identical parameter names,
-    shapes and torch default initialisers as the reference constructors); weights are only a starting point for
-    timing."""
-    from pytorch_generative_b200 import models
+def _thread_sweep(spec, candidates):
+    """Picks the intra-op thread count for the CPU arm: one forward + backward of a depth-reduced copy of the model
+    (2 blocks / layers, same widths, batch 1) at each candidate count; torch's CPU pool stops scaling -- and on a
+    128-thread host gets slower -- well below the core count on this workload, so "all cores"  is
+    resolved to the fastest measured count, and the sweep is reported next to the result."""
+    from oracle import reference_path as O
 
-    torch.manual_seed(0)
-    m = getattr(models, spec["cls"])(**spec["cfg"])
-    return {k: v.detach().clone() for k, v in m.state_dict().items()}
+    cfg = dict(spec["cfg"])
+    for k in ("n_transformer_blocks", "n_residual", "n_gated", "n_pixel_snail_blocks"):
+        if k in cfg:
+            cfg[k] = min(cfg[k], 2)
+    state = O.init_state(spec["oracle"], cfg)
+    x = synthetic_batch(1, spec["shape"], seed=0)
+    out = {}
+    for t in candidates:
+        torch.set_num_threads(t)
+        best = float("inf")
+        for _ in range(2):
+            t0 = time.perf_counter()
+            O.loss_and_grads(spec["oracle"], state, x, cfg)
+            best = min(best, time.perf_counter() - t0)
+        out[t] = round(best * 1e3, 1)
+    return out
 
 
-def cpu_baseline(spec, steps, warmup, budget_s=45.0):
-    """Times the oracle port on the host cores; bounded: stops adding steps once `budget_s` is spent."""
+def cpu_baseline(spec, steps, warmup, budget_s=60.0):
+    """Times the reference's CPU path (the oracle port: the same torch ops in the same order, bit-identical to the live
+    reference on this torch build, tests/test_oracle.py) on the host cores at BASELINE.md §4's reduced batch; bounded:
+    stops adding steps once `budget_s` is spent."""
     from oracle import reference_path as O
 
     try:
         avail = len(os.sched_getaffinity(0))
     except AttributeError:
         avail = os.cpu_count() or 1
-    # torch's intra-op pool stops scaling (and oversubscribes shared hosts) far below 100+ threads on this
-    # workload; 32 is what the reference's own DataLoader-free step can use productively.
-    threads = max(1, min(avail, 32))
+    candidates = sorted({c for c in (8, 16, 32, 64, avail) if c <= avail})
+    sweep = _thread_sweep(spec, candidates)
+    threads = min(sweep, key=sweep.get)
     torch.set_num_threads(threads)
     nb = spec["cpu_batch"]
-    ts = O.TrainState(spec["oracle"], _oracle_state(spec), spec["cfg"], lr=spec["lr"])
+    ts = O.TrainState(spec["oracle"], O.init_state(spec["oracle"], spec["cfg"]), spec["cfg"], lr=spec["lr"])
     x = synthetic_batch(nb, spec["shape"], seed=0)
     times, t_start = [], time.perf_counter()
     for i in range(warmup + steps):
@@ -358,9 +377,10 @@ def cpu_baseline(spec, steps, warmup, budget_s=45.0):
     timed = times[warmup:] if len(times) > warmup else times[-1:]
     dt = sum(timed) / len(timed)
     return {"value": round(nb / dt, 4), "unit": "images/sec", "cores": threads, "host_cores": avail, "kind": "port",
-            "ms_per_step": round(dt * 1e3, 1),
+            "ms_per_step": round(dt * 1e3, 1), "thread_sweep_ms": {str(k): v for k, v in sweep.items()},
             "sample": f"{len(timed)} timed step(s) after {min(warmup, len(times) - len(timed))} warm-up of the same training "
-                      f"step at batch {nb} on the host CPU (oracle/reference_path.py = the reference's torch-CPU fp32 path)"}
+                      f"step at batch {nb} on the host CPU (oracle/reference_path.py = the reference's torch-CPU fp32 path); "
+                      f"threads = fastest of a sweep over {candidates} on a 2-block copy of the model"}
 
 
 def run_reference(args):

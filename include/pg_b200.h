@@ -29,6 +29,9 @@ int pg_abi_version(void);
 const char* pg_last_error(void);
 /* Number of SMs of the current device (148 on B200); used by callers to size split-K. */
 int pg_sm_count(void);
+/* Leaves `n` SMs out of every persistent grid from now on (returns the previous setting; 0 = use them all): room for the
+ * NCCL kernels of the gradient all-reduce that run concurrently with the backward pass under data parallelism. */
+int pg_reserve_sms(int n);
 /* Number of kernels this library has launched in this process (all threads); bench.py's gpu_launches. */
 unsigned long long pg_launch_count(void);
 
@@ -143,6 +146,12 @@ int pg_layernorm_bwd(const void* dy_bf16, const float* dy_f32, const float* x, c
 int pg_gated_act_fwd(const void* x, int x_is_f32, int P, int C, int act, void* y, int y_is_f32, void* stream);
 int pg_gated_act_bwd(const void* x, int x_is_f32, const void* dy, int dy_is_f32, int P, int C, int act,
                      void* dx, int dx_is_f32, void* stream);
+/* y = res + act(x[:, :C]) * sigmoid(x[:, C:]) in one pass: the residual sum around PixelSNAIL's gated residual block
+ * (reference pixel_snail.py:52-56), res / y fp32 [P, C]. */
+int pg_gated_res_fwd(const void* x, int x_is_f32, const float* res, int P, int C, int act, float* y, void* stream);
+/* out = bf16(dy * act'(pre)) given the ACTIVATED value ya = act(pre) (relu / elu; elu'(pre) = ya + 1 for pre <= 0): the
+ * backward of an activation whose output, not input, was kept (elu(conv(.)) outputs, pixel_snail.py:27-28,115-119). */
+int pg_dact_from_out(const void* dy, int dy_is_f32, const void* ya_bf16, int64_t numel, int act, void* out_bf16, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Recipe loss — reference models/autoregressive/image_gpt.py:158-162 (identical in the other three):

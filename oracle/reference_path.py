@@ -251,6 +251,94 @@ def forward(model, p, x, cfg=None):
 
 
 # --------------------------------------------------------------------------------------------------
+# Parameter layout of the four constructors (state-dict keys and shapes, torch default initialisers)
+# --------------------------------------------------------------------------------------------------
+def init_state(model, cfg, seed=0):
+    """A freshly initialised state dict of `model` with the reference's keys and shapes and the same
+    torch initialisers its constructors use (nn.Conv2d / nn.LayerNorm defaults, `_pos` zeros): what
+    `Model(**cfg).state_dict()` returns in the reference (pixel_cnn.py:59-104, gated_pixel_cnn.py:136-183,
+    pixel_snail.py:130-180, image_gpt.py:64-103).  Used by the CPU timing arm, which must not import the product."""
+    torch.manual_seed(seed)
+    sd = {}
+
+    def conv(name, cin, cout, k=1):
+        m = torch.nn.Conv2d(cin, cout, k)
+        sd[name + ".weight"], sd[name + ".bias"] = m.weight.detach().clone(), m.bias.detach().clone()
+
+    def causal(name, cin, cout, k, mask_center):
+        conv(name, cin, cout, k)
+        kh, kw = sd[name + ".weight"].shape[-2:]
+        sd[name + ".mask"] = causal_mask(kh, kw, mask_center).expand_as(sd[name + ".weight"]).clone()
+
+    def ln(name, c):
+        sd[name + ".weight"], sd[name + ".bias"] = torch.ones(c), torch.zeros(c)
+
+    def attention(pre, cin, embed, out, extra=0):
+        conv(pre + "_q", cin, embed)
+        conv(pre + "_kv", cin + extra, embed + out)
+        conv(pre + "_proj", out, out)
+
+    if model == "pixel_cnn":
+        c, res = cfg["in_channels"], cfg.get("residual_channels", 128)
+        causal("_input", c, 2 * res, 7, True)
+        for i in range(cfg.get("n_residual", 15)):
+            pre = f"_causal_layers.{i}._net."
+            conv(pre + "1", 2 * res, res)
+            causal(pre + "3", res, res, 3, False)
+            conv(pre + "5", res, 2 * res)
+        conv("_head.1", 2 * res, cfg.get("head_channels", 32))
+        conv("_head.3", cfg.get("head_channels", 32), cfg["out_channels"])
+    elif model == "gated_pixel_cnn":
+        g = cfg.get("gated_channels", 128)
+
+        def layer(pre, cin, k):
+            conv(pre + "_vstack_1xN", cin, g, (1, k))
+            conv(pre + "_vstack_Nx1", g, 2 * g, (k // 2 + 1, 1))
+            conv(pre + "_vstack_1x1", cin, 2 * g)
+            conv(pre + "_link", 2 * g, 2 * g)
+            conv(pre + "_hstack_1xN", cin, 2 * g, (1, k // 2 + 1))
+            conv(pre + "_hstack_residual", g, g)
+            conv(pre + "_hstack_skip", g, g)
+
+        layer("_input.", cfg["in_channels"], 7)
+        for i in range(cfg.get("n_gated", 10)):
+            layer(f"_gated_layers.{i}.", g, 3)
+        conv("_head.1", g, cfg.get("head_channels", 32))
+        conv("_head.3", cfg.get("head_channels", 32), cfg["out_channels"])
+    elif model == "pixel_snail":
+        c, img = cfg.get("n_channels", 64), cfg["in_channels"]
+        key, val = cfg.get("attention_key_channels", 4), cfg.get("attention_value_channels", 32)
+        causal("_input", img, c, 3, True)
+        for i in range(cfg.get("n_pixel_snail_blocks", 8)):
+            pre = f"_pixel_snail_blocks.{i}."
+            for j in range(cfg.get("n_residual_blocks", 2)):
+                conv(f"{pre}_residual.{j}._input_conv", c, c, 2)
+                conv(f"{pre}_residual.{j}._output_conv", c, 2 * c, 2)
+            attention(pre + "_attention.", c + 2, key, val, extra=img)
+            conv(pre + "_residual_out", c, c)
+            conv(pre + "_attention_out", val, c)
+            conv(pre + "_out", c, c)
+        conv("_output.0", c, c // 2)
+        conv("_output.1", c // 2, cfg["out_channels"])
+    elif model == "image_gpt":
+        c, s = cfg.get("n_embedding_channels", 16), cfg.get("in_size", 28)
+        sd["_pos"] = torch.zeros(1, cfg["in_channels"], s, s)
+        causal("_input", cfg["in_channels"], c, 3, True)
+        for i in range(cfg.get("n_transformer_blocks", 8)):
+            pre = f"_transformer.{i}."
+            ln(pre + "_ln1", c)
+            ln(pre + "_ln2", c)
+            attention(pre + "_attn.", c, c, c)
+            conv(pre + "_out.0", c, 4 * c)
+            conv(pre + "_out.2", 4 * c, c)
+        ln("_ln", c)
+        conv("_out", c, cfg["out_channels"])
+    else:
+        raise ValueError(model)
+    return sd
+
+
+# --------------------------------------------------------------------------------------------------
 # Recipe loss, training step, sampling
 # --------------------------------------------------------------------------------------------------
 

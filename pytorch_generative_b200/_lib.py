@@ -58,6 +58,8 @@ _SIGNATURES = {
     "pg_layernorm_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "pg_gated_act_fwd": [_vp, _i32, _i32, _i32, _i32, _vp, _i32, _vp],
     "pg_gated_act_bwd": [_vp, _i32, _vp, _i32, _i32, _i32, _i32, _vp, _i32, _vp],
+    "pg_gated_res_fwd": [_vp, _i32, _vp, _i32, _i32, _i32, _vp, _vp],
+    "pg_dact_from_out": [_vp, _i32, _vp, _i64, _i32, _vp, _vp],
     "pg_bce_logits_fwd_bwd": [_vp, _vp, _i64, _f32, _vp, _vp, _vp],
     "pg_nchw_to_pm": [_vp, _i32, _i32, _i32, _vp, _i32, _i64, _vp],
     "pg_pm_to_nchw": [_vp, _i32, _i64, _i32, _i32, _i32, _i32, _vp, _vp],
@@ -80,7 +82,8 @@ _SIGNATURES = {
     "pg_tap_gather": [_vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _vp],
     "pg_tap_scatter": [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _i64, _vp, _vp, _i64, _vp],
 }
-EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + ["pg_abi_version", "pg_last_error", "pg_sm_count", "pg_launch_count"])
+EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + ["pg_abi_version", "pg_last_error", "pg_sm_count", "pg_launch_count",
+                                                 "pg_reserve_sms"])
 
 _lib = None
 
@@ -176,6 +179,17 @@ def sm_count():
     if _sm_count is None:
         _sm_count = load().pg_sm_count()
     return _sm_count
+
+
+def reserve_sms(n):
+    """SMs left out of the persistent grids (see pg_reserve_sms); returns the previous setting."""
+    global _sm_count
+    lib = load()
+    lib.pg_reserve_sms.restype = ctypes.c_int
+    lib.pg_reserve_sms.argtypes = [ctypes.c_int]
+    old = lib.pg_reserve_sms(int(n))
+    _sm_count = None
+    return old
 
 
 # ------------------------------------------------------------------------------------------------
@@ -315,6 +329,23 @@ def gated_act_fwd(x, y, act):
     assert x.is_contiguous() and y.is_contiguous() and y.shape == (P, C2 // 2)
     _check(lib.pg_gated_act_fwd(_ptr(x), int(x.dtype == torch.float32), P, C2 // 2, act, _ptr(y),
                                 int(y.dtype == torch.float32), _stream()), "pg_gated_act_fwd")
+
+
+@_device_guarded
+def gated_res_fwd(x, res, y, act):
+    """y = res + act(x[:, :C]) * sigmoid(x[:, C:]); res, y fp32 [P, C]."""
+    P, C2 = x.shape
+    assert x.is_contiguous() and res.is_contiguous() and y.is_contiguous() and res.dtype == y.dtype == torch.float32
+    _check(load().pg_gated_res_fwd(_ptr(x), int(x.dtype == torch.float32), _ptr(res), P, C2 // 2, act, _ptr(y), _stream()),
+           "pg_gated_res_fwd")
+
+
+@_device_guarded
+def dact_from_out(dy, ya, act, out):
+    """out = bf16(dy * act'(pre)) with ya = act(pre) (relu / elu)."""
+    assert dy.is_contiguous() and ya.is_contiguous() and out.is_contiguous() and ya.dtype == out.dtype == torch.bfloat16
+    _check(load().pg_dact_from_out(_ptr(dy), int(dy.dtype == torch.float32), _ptr(ya), dy.numel(), act, _ptr(out), _stream()),
+           "pg_dact_from_out")
 
 
 @_device_guarded

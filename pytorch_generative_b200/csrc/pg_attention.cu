@@ -14,6 +14,11 @@
 #include "../../include/pg_b200.h"
 #include "pg_common.cuh"
 
+static long long* g_attn_trace = nullptr;
+// Development hook: a device buffer of >= 4 * 4096 int64 that block 0 of the backward kernel fills with clock64() stamps
+// (role r, event slot: trace[r * 4096 + k], see tools/attn_trace.py); nullptr switches it off.  Not part of the supported ABI.
+extern "C" void pg_debug_set_trace(void* buf) { g_attn_trace = reinterpret_cast<long long*>(buf); }
+
 namespace {
 
 constexpr int MAX_S = 1024;   // per-warp score buffer (floats) in shared memory
@@ -29,6 +34,7 @@ struct AttnArgs {
   float* dq_accum;
   int N, S, H, dk, dv, strict;
   float scale;
+  long long* trace;  // pg_debug_set_trace: clock64 timeline of block 0 (development only)
   int dbg;  // PG_ATTN_DEBUG (timing experiments only): 1 = no MMAs issued, 2 = no softmax-thread arithmetic,
             // 3 = dQ drain without the TMA reduce, 4 = dQ drain reads TMEM only, 5 = no P / dS stores (and fences),
             // 6 = no MUFU, 7 = no fence.proxy.async
@@ -332,6 +338,7 @@ extern "C" int pg_causal_attn_bwd(const void* q, int64_t ld_q, const void* k, in
   {
     static const char* dbg = getenv("PG_ATTN_DEBUG");
     a.dbg = dbg ? atoi(dbg) : 0;
+    a.trace = g_attn_trace;
   }
   const long long total = (long long)N * H * S;
   const int lanes_per = dv / 8;

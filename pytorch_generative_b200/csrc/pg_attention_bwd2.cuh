@@ -149,6 +149,17 @@ attn_bwd2_kernel(const __grid_constant__ AttnTmaps tm, const AttnArgs a, const i
 
   Bwd2Cursor c;
   bwd2_item(c, 0, a, T);
+  // development timeline (build with -DPG_ATTN_TRACE; pg_debug_set_trace, tools/attn_trace.py): role r stamps clock64()
+  // into trace[r * 4096 + k].  Compiled out by default: the volatile clock reads pin the instruction schedule around
+  // every wait (measured: 572 vs 501 us per call with the stamps compiled in but switched off).
+#ifdef PG_ATTN_TRACE
+  int tr_n = 0;
+  auto TR = [&](int role) {
+    if (a.trace != nullptr && blockIdx.x == 0 && lane == 0 && tr_n < 4096) a.trace[role * 4096 + tr_n++] = clock64();
+  };
+#else
+  auto TR = [](int) {};
+#endif
 
   if (warp == W_TMA) {
     // ===================== TMA producer (whole warp converged, one elected lane issues) =====================
@@ -167,9 +178,11 @@ attn_bwd2_kernel(const __grid_constant__ AttnTmaps tm, const AttnArgs a, const i
         const int i = c.j + c.it;
         const unsigned qs = g % C::NQ, os = g % C::NDO;
         mbar_wait(&q_empty[qs], ((g / C::NQ) & 1u) ^ 1u);
+        TR(0);
         mbar_arrive_expect_tx_w(&q_full[qs], ATOM_BYTES);
         tma_load_3d_w(sQ + qs * ATOM_BYTES, &tm.q, &q_full[qs], c.h * 64, i * AT, c.n);
         mbar_wait(&do_empty[os], ((g / C::NDO) & 1u) ^ 1u);
+        TR(0);
         mbar_arrive_expect_tx_w(&do_full[os], V_BYTES);
 #pragma unroll
         for (int v = 0; v < DV / 64; ++v)
@@ -233,7 +246,9 @@ attn_bwd2_kernel(const __grid_constant__ AttnTmaps tm, const AttnArgs a, const i
         const uint64_t q_mn = umma_desc_sw128(q_of(g), ATOM_BYTES, 1024), do_mn = umma_desc_sw128(do_of(g), ATOM_BYTES, 1024);
         const uint64_t k_mn = umma_desc_sw128(k_of(m), ATOM_BYTES, 1024);
 
+        TR(1);
         mbar_wait(p_full, g & 1u);  // P(g) published; S is free
+        TR(1);
         tc_fence_after();
         if (nx.valid && !defer) issue_s(g + 1, mn, crosses);
         if (first) {  // the previous item's dV / dK have been read out
@@ -248,7 +263,9 @@ attn_bwd2_kernel(const __grid_constant__ AttnTmaps tm, const AttnArgs a, const i
         umma_commit_w(p_free);
         umma_commit_w(&do_empty[g % C::NDO]);
 
+        TR(1);
         mbar_wait(ds_full, g & 1u);  // dS(g) published; dP is free
+        TR(1);
         tc_fence_after();
         if (mma_on) {
 #pragma unroll
@@ -258,7 +275,9 @@ attn_bwd2_kernel(const __grid_constant__ AttnTmaps tm, const AttnArgs a, const i
         umma_commit_w(&q_empty[g % C::NQ]);
         if (nx.valid && !defer) issue_dp(g + 1, mn);
         const unsigned b = g % C::NDQ;
+        TR(1);
         mbar_wait(&dq_empty[b], ((g / C::NDQ) & 1u) ^ 1u);
+        TR(1);
         tc_fence_after();
         if (mma_on) {
 #pragma unroll
@@ -289,7 +308,9 @@ attn_bwd2_kernel(const __grid_constant__ AttnTmaps tm, const AttnArgs a, const i
     while (c.valid) {
       const unsigned b = g % C::NDQ;
       const int i = c.j + c.it;
+      TR(2);
       mbar_wait(&dq_full[b], (g / C::NDQ) & 1u);
+      TR(2);
       tc_fence_after();
       if (a.dbg != 4) {
 #pragma unroll
@@ -402,7 +423,9 @@ attn_bwd2_kernel(const __grid_constant__ AttnTmaps tm, const AttnArgs a, const i
       load_stats(nx);  // in flight underneath this tile
 
       // ---- stage A: S -> P ----
+      if (warp == 0) TR(3);
       mbar_wait(s_full, g & 1u);
+      if (warp == 0) TR(3);
       tc_fence_after();
       uint32_t pk[NCH][16];
       const bool work = a.dbg != 2;
@@ -435,7 +458,9 @@ attn_bwd2_kernel(const __grid_constant__ AttnTmaps tm, const AttnArgs a, const i
         if (need_mask) p_tile(std::true_type{});
         else p_tile(std::false_type{});
       }
+      if (warp == 0) TR(3);
       if (g > 0) mbar_wait(p_free, (g - 1) & 1u);  // dV(g-1) no longer reads sP
+      if (warp == 0) TR(3);
       if (work && a.dbg != 5) {
 #pragma unroll
         for (int cc = 0; cc < NCH; ++cc) store_tile_row_chunk(sP, r, grp * NCH + cc, pk[cc]);
@@ -446,7 +471,9 @@ attn_bwd2_kernel(const __grid_constant__ AttnTmaps tm, const AttnArgs a, const i
       if (lane == 0) mbar_arrive(p_full);
 
       // ---- stage B: dP -> dS = P (dP - delta) ----
+      if (warp == 0) TR(3);
       mbar_wait(dp_full, g & 1u);
+      if (warp == 0) TR(3);
       tc_fence_after();
       if (work) {
         uint32_t dv[NCH][32];
@@ -464,7 +491,9 @@ attn_bwd2_kernel(const __grid_constant__ AttnTmaps tm, const AttnArgs a, const i
           }
         }
       }
+      if (warp == 0) TR(3);
       if (g > 0) mbar_wait(ds_free, (g - 1) & 1u);  // dK(g-1), dQ(g-1) no longer read sdS
+      if (warp == 0) TR(3);
       if (work && a.dbg != 5) {
 #pragma unroll
         for (int cc = 0; cc < NCH; ++cc) store_tile_row_chunk(sdS, r, grp * NCH + cc, pk[cc]);

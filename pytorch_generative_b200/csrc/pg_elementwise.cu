@@ -296,9 +296,20 @@ ln_bwd_generic_kernel(const void* __restrict__ dy_, const float* __restrict__ x,
 // GatedActivation (reference nn/convolution.py:62-66).  8 channels per thread.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
+// One-MUFU forms for bf16 outputs (tanh.approx: max relative error 2^-11, below the 2^-9 of the bf16 result):
+// sigmoid(x) = 0.5 tanh(x / 2) + 0.5.  The fp32-in / fp32-out module path keeps the exact functions (1e-3 parity).
+template <bool FAST>
+__device__ __forceinline__ float gate_sigmoid(float x) {
+  return FAST ? fmaf(0.5f, pg_tanh_fast(0.5f * x), 0.5f) : sigmoidf_(x);
+}
+template <bool FAST>
+__device__ __forceinline__ float gate_act(int act, float x) {
+  return (FAST && act == PG_ACT_TANH) ? pg_tanh_fast(x) : pg_act_fwd(act, x);
+}
 
 template <typename TX, typename TY>
-__global__ void gated_fwd_kernel(const TX* __restrict__ x, int P, int C, int act, TY* __restrict__ y) {
+__global__ void gated_fwd_kernel(const TX* __restrict__ x, int P, int C, int act, TY* __restrict__ y,
+                                 const float* __restrict__ res = nullptr) {
   const int cg = C / 8;
   const long long total = (long long)P * cg;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -309,7 +320,15 @@ __global__ void gated_fwd_kernel(const TX* __restrict__ x, int P, int C, int act
     load8<TX>(x + row * 2 * C + c, f);
     load8<TX>(x + row * 2 * C + C + c, g);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) o[i] = pg_act_fwd(act, f[i]) * sigmoidf_(g[i]);
+    constexpr bool FAST = sizeof(TX) == 2;  // bf16 pre-activations (the fused stacks)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = gate_act<FAST>(act, f[i]) * gate_sigmoid<FAST>(g[i]);
+    if (res) {  // residual stream fused: y = res + gate(x)
+      float rr[8];
+      load8<float>(res + row * C + c, rr);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] += rr[i];
+    }
     store8<TY>(y + row * C + c, o);
   }
 }
@@ -327,10 +346,14 @@ __global__ void gated_bwd_kernel(const TX* __restrict__ x, const TDY* __restrict
     load8<TX>(x + row * 2 * C + C + c, g);
     load8<TDY>(dy + row * C + c, d);
 #pragma unroll
+    constexpr bool FAST = sizeof(TX) == 2;
+#pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const float s = sigmoidf_(g[i]);
-      df[i] = d[i] * s * pg_act_bwd(act, f[i]);
-      dgt[i] = d[i] * pg_act_fwd(act, f[i]) * s * (1.f - s);
+      const float s = gate_sigmoid<FAST>(g[i]);
+      const float a = gate_act<FAST>(act, f[i]);
+      const float da = (FAST && act == PG_ACT_TANH) ? fmaf(-a, a, 1.f) : pg_act_bwd(act, f[i]);
+      df[i] = d[i] * s * da;
+      dgt[i] = d[i] * a * s * (1.f - s);
     }
     store8<TDX>(dx + row * 2 * C + c, df);
     store8<TDX>(dx + row * 2 * C + C + c, dgt);
@@ -516,6 +539,20 @@ act_cast_kernel(const TI* __restrict__ x, int64_t ld_x, int P, int C, int act, b
   }
 }
 
+// out = bf16(dy * act'(pre)) where `ya` holds the ACTIVATED value act(pre) (relu / elu): one pass.
+template <typename TDY>
+__global__ void __launch_bounds__(256)
+dact_out_kernel(const TDY* __restrict__ dy, const bf16* __restrict__ ya, long long numel8, int dact, bf16* __restrict__ out) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < numel8; i += (long long)gridDim.x * blockDim.x) {
+    float d[8], a[8], o[8];
+    load8<TDY>(dy + i * 8, d);
+    load8<bf16>(ya + i * 8, a);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = d[j] * pg_act_bwd(dact, a[j]);
+    store8<bf16>(out + i * 8, o);
+  }
+}
+
 int grid_for(long long work_items, int threads, int max_blocks_per_sm = 16) {
   long long b = (work_items + threads - 1) / threads;
   long long cap = (long long)pg_num_sms() * max_blocks_per_sm;
@@ -606,15 +643,40 @@ extern "C" int pg_gated_act_fwd(const void* x, int x_is_f32, int P, int C, int a
   return pg_check_launch("pg_gated_act_fwd");
 }
 
+extern "C" int pg_gated_res_fwd(const void* x, int x_is_f32, const float* res, int P, int C, int act, float* y, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  PG_REQUIRE(x && res && y && P > 0 && C > 0 && C % 8 == 0, "pg_gated_res_fwd: null/empty argument or C %% 8 != 0");
+  const int threads = 256;
+  const int blocks = grid_for((long long)P * (C / 8), threads);
+  if (x_is_f32) gated_fwd_kernel<float, float><<<blocks, threads, 0, stream>>>((const float*)x, P, C, act, y, res);
+  else gated_fwd_kernel<bf16, float><<<blocks, threads, 0, stream>>>((const bf16*)x, P, C, act, y, res);
+  return pg_check_launch("pg_gated_res_fwd");
+}
+
+extern "C" int pg_dact_from_out(const void* dy, int dy_is_f32, const void* ya_bf16, int64_t numel, int act, void* out_bf16,
+                                void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  PG_REQUIRE(dy && ya_bf16 && out_bf16 && numel > 0 && numel % 8 == 0, "pg_dact_from_out: null argument or numel %% 8 != 0");
+  PG_REQUIRE(act == PG_ACT_RELU || act == PG_ACT_ELU, "pg_dact_from_out: relu / elu only");
+  const int dact = act == PG_ACT_RELU ? PG_ACT_RELU_OUT : PG_ACT_ELU_OUT;
+  const int blocks = grid_for(numel / 8, 256);
+  if (dy_is_f32) dact_out_kernel<float><<<blocks, 256, 0, stream>>>((const float*)dy, (const bf16*)ya_bf16, numel / 8, dact, (bf16*)out_bf16);
+  else dact_out_kernel<bf16><<<blocks, 256, 0, stream>>>((const bf16*)dy, (const bf16*)ya_bf16, numel / 8, dact, (bf16*)out_bf16);
+  return pg_check_launch("pg_dact_from_out");
+}
+
 extern "C" int pg_gated_act_bwd(const void* x, int x_is_f32, const void* dy, int dy_is_f32, int P, int C, int act,
                                 void* dx, int dx_is_f32, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   PG_REQUIRE(x && dy && dx && P > 0 && C > 0, "pg_gated_act_bwd: null/empty argument");
   PG_REQUIRE(C % 8 == 0, "pg_gated_act_bwd: C=%d must be a multiple of 8", C);
-  PG_REQUIRE(x_is_f32 == dy_is_f32 && x_is_f32 == dx_is_f32, "pg_gated_act_bwd: mixed dtypes not supported");
+  PG_REQUIRE(x_is_f32 == dx_is_f32 && (x_is_f32 == dy_is_f32 || (!x_is_f32 && dy_is_f32)),
+             "pg_gated_act_bwd: dx has x's dtype; dy has x's dtype or is fp32 over a bf16 x");
   const int threads = 256;
   const int blocks = grid_for((long long)P * (C / 8), threads);
-  if (x_is_f32)
+  if (!x_is_f32 && dy_is_f32)  // bf16 pre-activation, fp32 gradient of a residual stream
+    gated_bwd_kernel<bf16, float, bf16><<<blocks, threads, 0, stream>>>((const bf16*)x, (const float*)dy, P, C, act, (bf16*)dx);
+  else if (x_is_f32)
     gated_bwd_kernel<float, float, float><<<blocks, threads, 0, stream>>>((const float*)x, (const float*)dy, P, C, act,
                                                                           (float*)dx);
   else

@@ -31,7 +31,17 @@ int pg_check_launch(const char* what) {
 extern "C" int pg_abi_version(void) { return PG_ABI_VERSION; }
 extern "C" const char* pg_last_error(void) { return g_err; }
 
-int pg_num_sms() {
+// SMs the persistent kernels leave free (pg_reserve_sms): under data parallelism the NCCL all-reduce kernels of the
+// gradient buckets run next to the backward GEMMs; a persistent grid that claims every SM makes them queue behind it (or
+// pushes GEMM CTAs into a ragged second wave), so the grid is sized to what is left.
+static std::atomic<int> g_reserved_sms{0};
+extern "C" int pg_reserve_sms(int n) {
+  const int old = g_reserved_sms.load();
+  g_reserved_sms.store(n < 0 ? 0 : n);
+  return old;
+}
+
+static int device_sms() {
   static int cached[64] = {0};
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
@@ -41,6 +51,10 @@ int pg_num_sms() {
     cached[dev] = n;
   }
   return cached[dev];
+}
+int pg_num_sms() {
+  const int n = device_sms() - g_reserved_sms.load();
+  return n < 2 ? 2 : (n & ~1);  // an even count: the 2-CTA kernels launch whole pairs
 }
 extern "C" int pg_sm_count(void) { return pg_num_sms(); }
 extern "C" unsigned long long pg_launch_count(void) { return g_launches.load(); }

@@ -264,7 +264,8 @@ class ImageGPT(base.AutoregressiveModel):
         biases = [b for blk in blocks for b in (blk._attn._q.bias, blk._attn._kv.bias)]
         sig = (mats[0].data_ptr(), tuple(p._version for p in mats), tuple(p._version for p in biases))
         cache = self.__dict__.setdefault("_wcache", {})
-        if cache.get("sig") == sig:
+        capturing = mats[0].is_cuda and torch.cuda.is_current_stream_capturing()
+        if cache.get("sig") == sig and not capturing:  # inside a CUDA graph the casts must be captured kernels
             return cache["packed"]
         dev = mats[0].device
         cout = self._out.weight.shape[0]
@@ -297,8 +298,7 @@ class ImageGPT(base.AutoregressiveModel):
                             host_dst=torch.empty(len(mats), dtype=torch.int64).pin_memory(),
                             dst=torch.empty(len(mats), dtype=torch.int64, device=dev))
                 cache["plan"] = plan
-            for i, d in enumerate(dsts):
-                plan["host_dst"][i] = d.data_ptr()
+            plan["host_dst"].numpy()[:] = [d.data_ptr() for d in dsts]
             plan["dst"].copy_(plan["host_dst"], non_blocking=True)
             L.cast_multi(plan["src"], plan["dst"], plan["numel"], plan["chunks"], plan["n_chunks"], plan["chunk"])
             ball = torch.cat([b.detach() for b in biases])  # [blocks * 3C]: q | kv biases of every block
@@ -322,7 +322,8 @@ class ImageGPT(base.AutoregressiveModel):
                                              w1=ops.pack_weight(blk._out[0].weight), w2=ops.pack_weight(blk._out[2].weight),
                                              meta=meta, cols_v=cols_v))
             packed["wo"] = ops.pack_weight(self._out.weight)
-        cache["sig"], cache["packed"] = sig, packed
+        if not capturing:
+            cache["sig"], cache["packed"] = sig, packed
         return packed
 
     # ------------------------------------------------------------------------------------------------------------

@@ -36,7 +36,7 @@ class ResidualBlock(nn.Module):
         _, t = pm.conv(x_f, self._input_conv.weight, self._input_conv.bias, geom, (1, 1), in_act=ELU, xa=x_e, emit=ELU,
                        emit_mode=pm.PRE_GRAD, want_main=False)
         u, _ = pm.conv(t, self._output_conv.weight, self._output_conv.bias, geom, (1, 1), in_act=ELU, xa=t)
-        return x_f + pm.gated(u, NONE)
+        return pm.gated_res(u, x_f, NONE)
 
     def forward(self, x):
         out = self._input_conv(x, pre_act=ELU)       # conv(elu(x)), cropped to h x w

@@ -24,7 +24,7 @@ import torch
 
 from .. import _lib as L
 from .. import ops
-from .tapconv import conv_taps, pack_tap_weight
+from .tapconv import conv_taps, packed_tap_weight
 
 F32, BF16 = torch.float32, torch.bfloat16
 Geom = collections.namedtuple("Geom", "n h w")
@@ -130,6 +130,31 @@ def gated(x, act):
     return _Gated.apply(x.contiguous(), act)
 
 
+class _GatedRes(torch.autograd.Function):
+    """res + gate(x) in one pass (fp32 stream in / out); backward: d res = dy, d x = gate'(x) dy."""
+
+    @staticmethod
+    def forward(ctx, x, res, act):
+        y = torch.empty_like(res)
+        L.gated_res_fwd(x, res, y, act)
+        ctx.save_for_backward(x)
+        ctx.act = act
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = torch.empty_like(x)
+        L.gated_act_bwd(x, dy, dx, ctx.act)  # fp32 dy over a bf16 x is a supported combination
+        return dx, dy, None
+
+
+def gated_res(x, res, act):
+    """res + act(x[:, :C]) * sigmoid(x[:, C:]) -> fp32 [P, C]: a gated residual block's output stream."""
+    return _GatedRes.apply(x.contiguous(), res.contiguous(), act)
+
+
 # --------------------------------------------------------------------------------------------------
 # convolutions
 # --------------------------------------------------------------------------------------------------
@@ -175,7 +200,7 @@ class _Conv(torch.autograd.Function):
         cin_p = xa.shape[1]
         taps = conv_taps(kh, kw, padding[0], padding[1])
         pointwise = len(taps) == 1 and taps[0] == (0, 0)
-        wcat = pack_tap_weight(weight, cin_p)
+        wcat = packed_tap_weight(weight, cin_p)
         b = None if bias is None else bias.detach()
         want_act = emit is not None
         kw_out = dict(act=emit if want_act else L.ACT_NONE, res0=res, want_bf16=want_act,
@@ -203,9 +228,9 @@ class _Conv(torch.autograd.Function):
         T = len(taps)
         if dya is not None and emit_mode == POST and emit != L.ACT_NONE:
             # gradient w.r.t. the activated output: back through emit (relu / elu) from the activated value itself
-            a = ya
-            one = torch.ones((), dtype=a.dtype, device=a.device)
-            dya = dya * (torch.where(a > 0, one, a + 1) if emit == L.ACT_ELU else (a > 0).to(a.dtype))
+            d = torch.empty(ya.shape, dtype=BF16, device=ya.device)
+            L.dact_from_out(dya.contiguous(), ya, emit, d)
+            dya = d
         if dy is None:
             dy = dya
         elif dya is not None:

@@ -45,6 +45,28 @@ def pack_tap_weight(weight, cin_p):
     return ops.to_bf16(w.reshape(cout, kh * kw * cin_p))
 
 
+_PACK_CACHE = {}
+
+
+def packed_tap_weight(weight, cin_p):
+    """`pack_tap_weight` memoised on the Parameter's identity and version counter: the bf16 copy is rebuilt once per
+    optimizer step, not once per forward (eval, sampling and gradient accumulation reuse it)."""
+    if weight.is_cuda and torch.cuda.is_current_stream_capturing():
+        return pack_tap_weight(weight, cin_p)  # inside a CUDA graph the cast must be a captured kernel of every replay
+    key = (id(weight), cin_p)
+    hit = _PACK_CACHE.get(key)
+    sig = (weight._version, weight.data_ptr(), tuple(weight.shape))
+    if hit is not None and hit[0] == sig and hit[2]() is weight:
+        return hit[1]
+    import weakref
+
+    packed = pack_tap_weight(weight, cin_p)
+    if len(_PACK_CACHE) > 4096:
+        _PACK_CACHE.clear()
+    _PACK_CACHE[key] = (sig, packed, weakref.ref(weight))
+    return packed
+
+
 class _TapConvFn(torch.autograd.Function):
     """NCHW fp32 in / out; bf16 tensor-core contraction in between."""
 

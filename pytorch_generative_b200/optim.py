@@ -30,12 +30,12 @@ class FusedAdam(torch.optim.Optimizer):
         n_t = len(params)
         host_ptrs = torch.empty(4, n_t, dtype=torch.int64).pin_memory()
         plan = dict(
-            key=tuple(id(p) for p in params), n_chunks=len(chunks),
+            key=tuple(p.data_ptr() for p in params), n_chunks=len(chunks),
             numel=torch.tensor(numel, dtype=torch.int64, device=dev),
             chunks=torch.tensor(chunks, dtype=torch.int32, device=dev).contiguous(),
             partials=torch.empty(len(chunks), dtype=torch.float32, device=dev),
             norm_out=torch.zeros(2, dtype=torch.float32, device=dev),
-            host_ptrs=host_ptrs, dev_ptrs=torch.empty(4, n_t, dtype=torch.int64, device=dev))
+            host_ptrs=host_ptrs, host_np=host_ptrs.numpy(), dev_ptrs=torch.empty(4, n_t, dtype=torch.int64, device=dev))
         self._plan[gi] = plan
         return plan
 
@@ -66,16 +66,20 @@ class FusedAdam(torch.optim.Optimizer):
             if not p.grad.is_contiguous():
                 p.grad = p.grad.contiguous()
         plan = self._plan.get(0)
-        if plan is None or plan["key"] != tuple(id(p) for p in params):
+        if plan is None or plan["key"] != tuple(p.data_ptr() for p in params):
             plan = self._build_plan(0, params)
         states = [self._state_for(p) for p in params]
         if states[0]["step"].is_cuda:  # a checkpoint mapped onto the device: keep the counters on the host
             for st in states:
                 st["step"] = st["step"].cpu()
         hp = plan["host_ptrs"]
-        for i, (p, st) in enumerate(zip(params, states)):
-            hp[0, i], hp[1, i], hp[2, i], hp[3, i] = p.data_ptr(), p.grad.data_ptr(), st["exp_avg"].data_ptr(), st[
-                "exp_avg_sq"].data_ptr()
+        hn = plan["host_np"]  # numpy view of the pinned table: one vectorised fill per row, not a tensor index per entry
+        hn[1, :] = [p.grad.data_ptr() for p in params]
+        if plan.get("static_ok") != plan["key"]:  # parameter / moment addresses only change with the parameter set
+            hn[0, :] = [p.data_ptr() for p in params]
+            hn[2, :] = [st["exp_avg"].data_ptr() for st in states]
+            hn[3, :] = [st["exp_avg_sq"].data_ptr() for st in states]
+            plan["static_ok"] = plan["key"]
         plan["dev_ptrs"].copy_(hp, non_blocking=True)
         dp = plan["dev_ptrs"]
         L.grad_sqnorm(dp[1], plan["numel"], plan["chunks"], plan["n_chunks"], CHUNK, plan["partials"])

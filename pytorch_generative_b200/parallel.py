@@ -14,8 +14,27 @@ NVLink/NVSwitch.  Two mechanisms:
 The helpers are backend-agnostic (`gloo` on CPU in the tests).
 """
 
+import os
+
 import torch
 import torch.distributed as dist
+
+# SMs the persistent GEMM / attention grids leave to the NCCL kernels of the in-backward bucket all-reduces (world > 1)
+DEFAULT_RESERVED_SMS = 4
+
+
+# CTAs NCCL may use per collective.  One step moves 303 MB of gradients (C5) underneath ~40 ms of backward: a few GB/s, a
+# fraction of one NVLink; every CTA NCCL takes is an SM the persistent GEMM grid does not get (see pg_reserve_sms).
+DEFAULT_NCCL_MAX_CTAS = 4
+
+
+def configure_nccl():
+    """Call before `init_process_group`: caps NCCL's CTAs per collective (NCCL_MAX_CTAS; PG_NCCL_MAX_CTAS overrides, 0 keeps
+    NCCL's default)."""
+    n = int(os.environ.get("PG_NCCL_MAX_CTAS", str(DEFAULT_NCCL_MAX_CTAS)))
+    if n > 0:
+        os.environ.setdefault("NCCL_MAX_CTAS", str(n))
+        os.environ.setdefault("NCCL_MIN_CTAS", "1")
 
 
 def broadcast_parameters(module, src=0):
@@ -101,6 +120,11 @@ class OverlappedGradAverager:
         if self.world > 1 and hasattr(model, "set_grad_bucket_hook"):
             model.set_grad_bucket_hook(bucket_all_reduce_mean)
             bucketed = list(model.bucketed_parameters())
+            reserve = int(os.environ.get("PG_DP_RESERVE_SMS", str(DEFAULT_RESERVED_SMS)))
+            if bucketed and reserve > 0 and torch.cuda.is_available():
+                from . import _lib
+
+                _lib.reserve_sms(reserve)  # the bucket all-reduces run next to the backward GEMMs (see pg_reserve_sms)
         skip = {id(p) for p in bucketed}
         self.n_bucketed = len(bucketed)
         self.rest = FlatGradAverager([p for p in params if id(p) not in skip])

@@ -106,7 +106,7 @@ def test_overlay_rebinds_reference_names():
         try:
             assert ref.models.ImageGPT is models.ImageGPT and ref.nn.CausalAttention is nn.CausalAttention
             assert ref.models.autoregressive.pixel_snail.PixelSNAIL is models.PixelSNAIL
-            assert len(bound) == 5 + 2 * 4
+            assert len(bound) == 6 + 2 * 4  # 6 nn names (incl. LinearCausalAttention) + 4 models in 2 namespaces
             m = ref.models.PixelCNN(in_channels=1, out_channels=1, n_residual=1, residual_channels=4, head_channels=4)
             assert isinstance(m, models.PixelCNN)
         finally:

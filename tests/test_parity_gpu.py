@@ -395,3 +395,40 @@ def test_row_truncated_forward_is_bit_identical(pg, name):
         for r in (0, 3, 6):
             part = m(x[:, :, : r + 1].contiguous())
             assert torch.equal(part, full[:, :, : r + 1]), (name, r)
+
+
+def test_transformer_block_standalone_forward_matches_oracle(pg):
+    """`TransformerBlock(x)` on its own (reference image_gpt.py:50-52: h = x + attn(ln1(x)); h + mlp(ln2(h)))."""
+    from oracle import reference_path as O
+    from pytorch_generative_b200.models.image_gpt import TransformerBlock
+
+    torch.manual_seed(4)
+    blk = TransformerBlock(n_channels=64, n_attention_heads=4)
+    g = torch.Generator().manual_seed(5)
+    with torch.no_grad():
+        for p in blk.parameters():
+            p.add_(torch.randn(p.shape, generator=g) * 0.05)
+    x = torch.randn(2, 64, 8, 16, generator=g)
+    p = {k: v.detach() for k, v in blk.state_dict().items()}
+    a = O.nchw_layer_norm(x, p["_ln1.weight"], p["_ln1.bias"])
+    h = x + O.causal_attention(a, p, "_attn.", 4, 64, 64, False)
+    m = O.nchw_layer_norm(h, p["_ln2.weight"], p["_ln2.bias"])
+    ref = h + torch.nn.functional.conv2d(torch.nn.functional.gelu(torch.nn.functional.conv2d(m, p["_out.0.weight"], p["_out.0.bias"])),
+                                         p["_out.2.weight"], p["_out.2.bias"])
+    y = blk.to(dev())(x.to(dev()))
+    check("transformer block", y, ref, TOL_BF16)
+
+
+def test_image_gpt_eval_forward_keeps_no_activations(pg):
+    """Under torch.no_grad() (eval, sampling) the fused stack must not retain the per-block activations, and a second
+    backward through a consumed graph raises a clear error instead of a TypeError."""
+    m = pg.models.ImageGPT(in_channels=1, out_channels=1, in_size=8, n_transformer_blocks=2, n_attention_heads=2,
+                           n_embedding_channels=32).to(dev())
+    x = torch.rand(2, 1, 8, 8, device=dev())
+    with torch.no_grad():
+        y = m(x)
+    assert y.grad_fn is None and not y.requires_grad
+    y = m(x)
+    y.sum().backward(retain_graph=True)
+    with pytest.raises(RuntimeError, match="already consumed"):
+        y.sum().backward()
