@@ -10,6 +10,7 @@ Behavioural contract kept from the reference:
 """
 
 import abc
+import warnings
 
 import torch
 from torch import nn
@@ -90,9 +91,11 @@ class AutoregressiveModel(GenerativeModel):
                 with torch.cuda.graph(graph):
                     static_out = self.forward(static_in)
                 cache[key] = (graph, static_in, static_out)
-            except RuntimeError:  # capture not possible in this context: launch eagerly (same kernels)
+            except RuntimeError as exc:  # capture not possible in this context: launch eagerly (same kernels)
                 torch.cuda.synchronize()
                 cache[key] = None
+                warnings.warn(f"{type(self).__name__}.sample(): CUDA-graph capture failed, launching the forward eagerly: "
+                              f"{exc!r}", RuntimeWarning)
         entry = cache[key]
         if entry is None:
             return lambda: self.forward(canvas[:, :, :rows])

@@ -12,6 +12,9 @@ with every bias / activation / residual folded into a GEMM epilogue, the residua
 gradients kept in fp32, and bf16 used only for tensor-core operands.
 """
 
+import os
+import warnings
+
 import torch
 from torch import nn
 
@@ -138,7 +141,15 @@ class _ImageGPTStack(torch.autograd.Function):
         qkv_rows = sv["blocks"][0]["wqkv"].shape[0] if n_blocks else 0
         dvs = sv["blocks"][0]["meta"]["dv_slot"] if n_blocks else 0
         per_block = 4 * C * C + 4 * C * C + C * H * dvs + qkv_rows * C
-        arena = torch.zeros(n_blocks * per_block, dtype=F32, device=dev)
+        # ... followed by the small per-block gradients (LayerNorm dgamma / dbeta / column sums, bias gradients of the qkv
+        # and fc1 layers), which their kernels accumulate with atomics: they share the one memset too
+        per_small = 6 * C + qkv_rows + 4 * C
+        arena = torch.zeros(n_blocks * (per_block + per_small), dtype=F32, device=dev)
+        small_base = n_blocks * per_block
+
+        def carve_small(b, off, n):
+            start = small_base + b * per_small + off
+            return arena[start: start + n]
 
         def carve(b, off, rows, cols):
             start = b * per_block + off
@@ -147,6 +158,7 @@ class _ImageGPTStack(torch.autograd.Function):
         # data parallelism: each block's slice of the arena is handed to the bucket hook (an asynchronous all-reduce)
         # as soon as its last wgrad GEMM is queued; see parallel.OverlappedGradAverager
         bucket_hook = sv["hook"] if _arena_views_are_grads(sv) else None
+        bucket_blocks = max(1, int(os.environ.get("PG_DP_BUCKET_BLOCKS", "1")))  # transformer blocks per all-reduce
         pending = []
 
         for b in reversed(range(n_blocks)):
@@ -160,7 +172,7 @@ class _ImageGPTStack(torch.autograd.Function):
             ops.linear_wgrad(dx_b, blk["g"], dw2)
             grads[base_i + 12] = dw2.view(C, 4 * C, 1, 1)
             du = ops.linear_dgrad(dx_b, blk["w2"], aux=blk["u"], dact=L.ACT_GIVEN)
-            grads[base_i + 11] = ops.bias_grad(du)
+            grads[base_i + 11] = ops.bias_grad(du, out=carve_small(b, 6 * C + qkv_rows, 4 * C))
             dw1 = carve(b, 4 * C * C, 4 * C, C)
             ops.linear_wgrad(du, blk["a2"], dw1)
             grads[base_i + 10] = dw1.view(4 * C, C, 1, 1)
@@ -168,7 +180,8 @@ class _ImageGPTStack(torch.autograd.Function):
             del du
             # h receives: LN2 path + direct (x_new = ... + h)
             dh, dh_b, grads[base_i + 8], grads[base_i + 9], grads[base_i + 7] = ops.layernorm_bwd(
-                da2, blk["h"], ln2_w.detach(), blk["mean2"], blk["rstd2"], dres0=dx, want_colsum=True)
+                da2, blk["h"], ln2_w.detach(), blk["mean2"], blk["rstd2"], dres0=dx, want_colsum=True,
+                stats=carve_small(b, 3 * C, 3 * C).view(3, C))
             del da2
             # h = x + proj(attn)
             dwp = carve(b, 8 * C * C, C, H * dv_slot)
@@ -181,7 +194,7 @@ class _ImageGPTStack(torch.autograd.Function):
             ops.attn_bwd(q, k, v, blk["o"], do, blk["lse"], dqkv[:, : H * slot], dqkv[:, H * slot: 2 * H * slot],
                          dqkv[:, 2 * H * slot:], n, S, H, meta["dk"], dv_slot, False)
             del do
-            dbqkv = ops.bias_grad(dqkv)
+            dbqkv = ops.bias_grad(dqkv, out=carve_small(b, 6 * C, qkv_rows))
             dwqkv = carve(b, 8 * C * C + C * H * dv_slot, qkv_rows, C)
             ops.linear_wgrad(dqkv, blk["a1"], dwqkv)
             if meta["identity"]:  # heads fill their slots: plain slices of the fused gradient buffers
@@ -199,10 +212,13 @@ class _ImageGPTStack(torch.autograd.Function):
             del dqkv
             # x receives: LN1 path + direct from h (dh) + direct from x_new (dx)
             dx, dx_b, grads[base_i + 0], grads[base_i + 1], dx_sum = ops.layernorm_bwd(
-                da1, blk["xs"], ln1_w.detach(), blk["mean1"], blk["rstd1"], dres0=dx, dres1=dh, want_colsum=True)
+                da1, blk["xs"], ln1_w.detach(), blk["mean1"], blk["rstd1"], dres0=dx, dres1=dh, want_colsum=True,
+                stats=carve_small(b, 0, 3 * C).view(3, C))
             del da1, dh, dh_b
-            if bucket_hook is not None:
-                pending.append(bucket_hook(arena[b * per_block: (b + 1) * per_block]))
+            if bucket_hook is not None and b % bucket_blocks == 0:
+                # blocks b .. b + bucket_blocks - 1 are complete: one contiguous slice of the arena
+                hi = min(b + bucket_blocks, n_blocks)
+                pending.append(bucket_hook(arena[b * per_block: hi * per_block]))
             sv["blocks"][b] = None  # release this block's activations
 
         in_w = params[1]
@@ -428,6 +444,8 @@ class ImageGPT(base.AutoregressiveModel):
                 torch.cuda.synchronize()
                 st["graph"] = False  # capture unavailable here: launch the same step eagerly
                 st["graph_error"] = repr(exc)
+                warnings.warn("ImageGPT.sample(): CUDA-graph capture of the per-pixel step failed, launching it eagerly "
+                              f"(same kernels, ~3x slower): {exc!r}", RuntimeWarning)
         for row in range(h):
             for col in range(w):
                 st["patch"].copy_(xin[:, :, row: row + kh, col: col + kw])

@@ -5,11 +5,13 @@ the reference's `nn.Sequential`s are not separate ops here: each one is fused in
 (`pre_act`), so a block is three kernels-backed convs: 1x1, masked 3x3 (type B), 1x1.
 """
 
+import torch
 from torch import nn
 
 from .. import _lib as L
 from .. import nn as pg_nn
-from . import base
+from .. import ops
+from . import base, incremental
 
 RELU = L.ACT_RELU
 
@@ -36,8 +38,9 @@ class CausalResidualBlock(nn.Module):
         return x + t
 
 
-class PixelCNN(base.AutoregressiveModel):
-    """The PixelCNN model — constructor of reference pixel_cnn.py:59-104."""
+class PixelCNN(incremental.IncrementalSamplingMixin, base.AutoregressiveModel):
+    """The PixelCNN model — constructor of reference pixel_cnn.py:59-104.  `sample()` evaluates one pixel at a time on
+    line buffers (models/incremental.py) instead of one full forward per pixel."""
 
     def __init__(self, in_channels=1, out_channels=1, n_residual=15, residual_channels=128, head_channels=32,
                  sample_fn=None):
@@ -53,6 +56,49 @@ class PixelCNN(base.AutoregressiveModel):
             nn.ReLU(),
             pg_nn.TapConv2d(in_channels=head_channels, out_channels=out_channels, kernel_size=1),
         )
+
+    # ---- per-pixel program of the incremental sampler ----
+    def _incremental_ok(self, canvas):
+        c2 = self._input.weight.shape[0]
+        head = self._head[1].weight.shape[0]
+        return super()._incremental_ok(canvas) and c2 % 16 == 0 and head % 8 == 0
+
+    def _build_pixel_state(self, sp, c):
+        c_p = ops.round_up(c, 8)
+        half = self._input.weight.shape[0] // 2
+        kh, kw = self._input.weight.shape[2:]
+        self._taps_in = incremental.live_taps(self._input.mask[0, 0], kh // 2, kw // 2)
+        self._taps_b = incremental.live_taps(self._causal_layers[0]._net[3].mask[0, 0], 1, 1) if len(self._causal_layers) else []
+        image = sp.cache(c_p)
+        t1 = [sp.cache(half) for _ in self._causal_layers]
+        return dict(image=image, t1=t1, caches=[image, *t1], weights={}, c_p=c_p)
+
+    def _pack_pixel_weights(self):
+        self._input.weight.data *= self._input.mask
+        c_p = ops.round_up(self._input.weight.shape[1], 8)
+        w = {"in": incremental.pack_taps(self._input.weight, self._taps_in, c_p), "in_b": self._input.bias.detach().clone()}
+        for i, blk in enumerate(self._causal_layers):
+            n1, n3, n5 = blk._net[1], blk._net[3], blk._net[5]
+            n3.weight.data *= n3.mask
+            w[f"b{i}_1"], w[f"b{i}_1b"] = ops.pack_weight(n1.weight), n1.bias.detach().clone()
+            w[f"b{i}_3"], w[f"b{i}_3b"] = incremental.pack_taps(n3.weight, self._taps_b, n3.weight.shape[1]), n3.bias.detach().clone()
+            w[f"b{i}_5"], w[f"b{i}_5b"] = ops.pack_weight(n5.weight), n5.bias.detach().clone()
+        w["h1"], w["h1b"] = ops.pack_weight(self._head[1].weight), self._head[1].bias.detach().clone()
+        w["h3"], w["h3b"] = ops.pack_weight(self._head[3].weight), self._head[3].bias.detach().clone()
+        return w
+
+    def _pixel_program(self, sp, st):
+        W = st["weights"]
+        off_in = [(dy, dx) for _, _, dy, dx in self._taps_in]
+        off_b = [(dy, dx) for _, _, dy, dx in self._taps_b]
+        x = sp.linear(sp.gather(st["image"], off_in), W["in"], W["in_b"], f32=True)           # masked 7x7 on the image
+        for i in range(len(self._causal_layers)):
+            t1 = sp.linear(sp.act(x, RELU), W[f"b{i}_1"], W[f"b{i}_1b"], act=RELU)            # relu(1x1(relu(x)))
+            sp.write(st["t1"][i], t1)
+            t2 = sp.linear(sp.gather(st["t1"][i], off_b), W[f"b{i}_3"], W[f"b{i}_3b"], act=RELU)  # relu(causal 3x3)
+            x = sp.linear(t2, W[f"b{i}_5"], W[f"b{i}_5b"], res0=x, res1=x, f32=True)           # x + (x + net(x))
+        h1 = sp.linear(sp.act(x, RELU), W["h1"], W["h1b"], act=RELU)
+        return sp.linear(h1, W["h3"], W["h3b"], f32=True)
 
     def forward(self, x):
         x = self._input(x)

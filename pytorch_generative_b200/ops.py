@@ -195,12 +195,15 @@ def layernorm_fwd(x, gamma, beta, eps, want_bf16=True, want_f32=False):
     return yb, yf, mean, rstd
 
 
-def layernorm_bwd(dy, x, gamma, mean, rstd, dres0=None, dres1=None, want_bf16=True, want_f32=True, want_colsum=False):
-    """Returns (dx_f32 (+dres0+dres1), dx_bf16, dgamma, dbeta[, colsum(dx)])."""
+def layernorm_bwd(dy, x, gamma, mean, rstd, dres0=None, dres1=None, want_bf16=True, want_f32=True, want_colsum=False,
+                  stats=None):
+    """Returns (dx_f32 (+dres0+dres1), dx_bf16, dgamma, dbeta[, colsum(dx)]).  `stats`: optional zero-filled fp32 [3, C]
+    (a slice of the caller's gradient arena) that receives dgamma, dbeta and the column sums."""
     P, C = x.shape
     dxf = empty((P, C), F32, x) if want_f32 else None
     dxb = empty((P, C), BF16, x) if want_bf16 else None
-    stats = zeros((3, C), F32, x)  # dgamma, dbeta, column sums of dx: one memset
+    if stats is None:
+        stats = zeros((3, C), F32, x)  # dgamma, dbeta, column sums of dx: one memset
     L.layernorm_bwd(dy, x, gamma, mean, rstd, dres0=dres0, dres1=dres1, dx_f32=dxf, dx_bf16=dxb, dgamma=stats[0],
                     dbeta=stats[1], dx_colsum=stats[2] if want_colsum else None)
     if want_colsum:

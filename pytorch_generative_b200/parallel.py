@@ -19,13 +19,13 @@ import os
 import torch
 import torch.distributed as dist
 
-# SMs the persistent GEMM / attention grids leave to the NCCL kernels of the in-backward bucket all-reduces (world > 1)
-DEFAULT_RESERVED_SMS = 4
+# SMs the persistent GEMM / attention grids leave to the NCCL kernels of the in-backward bucket all-reduces (world > 1).
+# Measured on 2 x B200 (profiles/r02_bench_2gpu.txt): reserving SMs and / or capping NCCL's CTAs moves the step by < 1 % in
+# either direction, so both knobs default to "off"; they stay for A/B runs (PG_DP_RESERVE_SMS, PG_NCCL_MAX_CTAS).
+DEFAULT_RESERVED_SMS = 0
 
-
-# CTAs NCCL may use per collective.  One step moves 303 MB of gradients (C5) underneath ~40 ms of backward: a few GB/s, a
-# fraction of one NVLink; every CTA NCCL takes is an SM the persistent GEMM grid does not get (see pg_reserve_sms).
-DEFAULT_NCCL_MAX_CTAS = 4
+# CTAs NCCL may use per collective (0 = NCCL's own choice).
+DEFAULT_NCCL_MAX_CTAS = 0
 
 
 def configure_nccl():

@@ -301,6 +301,46 @@ def test_sampling_follows_reference_raster_order(pg, name):
     assert torch.equal(cs[:, :, : h // 2], fx["cond"][:, :, : h // 2])
 
 
+@pytest.mark.parametrize("cls,cfg,shape", [
+    ("PixelCNN", dict(in_channels=1, out_channels=1, n_residual=3, residual_channels=16, head_channels=32), (3, 1, 28, 28)),
+    ("PixelCNN", dict(in_channels=3, out_channels=3, n_residual=2, residual_channels=32, head_channels=16), (2, 3, 8, 16)),
+    ("PixelSNAIL", dict(in_channels=3, out_channels=3, n_channels=64, n_pixel_snail_blocks=2, n_residual_blocks=2,
+                        attention_key_channels=16, attention_value_channels=32), (2, 3, 16, 16)),
+    ("PixelSNAIL", dict(in_channels=1, out_channels=1, n_channels=32, n_pixel_snail_blocks=1, n_residual_blocks=1,
+                        attention_key_channels=4, attention_value_channels=128), (4, 1, 28, 28)),
+])
+def test_incremental_sampler_logits_match_the_full_forward(pg, cls, cfg, shape):
+    """Teacher-forced sampling: with every pixel given (conditioned_on >= 0) `sample()` still evaluates each pixel's
+    logits on the line buffers / K/V caches; they must equal the full forward's logits of the same image.  Run twice:
+    the second call replays the captured per-pixel graph on reset caches and re-packed weights."""
+    torch.manual_seed(7)
+    m = getattr(pg.models, cls)(**cfg).to(dev())
+    with torch.no_grad():
+        for p in m.parameters():
+            p.mul_(1.5)
+    x = torch.bernoulli(torch.full(shape, 0.5)).to(dev())
+    with torch.no_grad():
+        ref = m(x)
+    n, c, h, w = shape
+    assert m._incremental_ok(x)
+    for rep in range(2):
+        seen = []
+        m._sample_fn = lambda logits: (seen.append(logits.detach().clone()), torch.zeros_like(logits))[1]
+        out = m.sample(conditioned_on=x)
+        assert torch.equal(out, x)
+        got = torch.stack(seen, dim=-1).view(n, c, h, w)
+        check(f"incremental logits (call {rep})", got, ref, TOL_BF16)
+    assert m._pixel_states and all(st["graph"] for st in m._pixel_states.values()), "per-pixel program was not graph-captured"
+
+
+def test_incremental_sampler_falls_back_beyond_its_row_limit(pg):
+    m = pg.models.PixelCNN(in_channels=1, out_channels=1, n_residual=1, residual_channels=8, head_channels=8).to(dev())
+    x = torch.bernoulli(torch.full((33, 1, 4, 4), 0.5)).to(dev())
+    m(x)
+    assert not m._incremental_ok(x)
+    assert torch.equal(m.sample(conditioned_on=x), x)
+
+
 @pytest.mark.parametrize("name,cls,cfg,shape", [
     ("pixel_cnn", "PixelCNN", dict(in_channels=1, out_channels=1, n_residual=3, residual_channels=32, head_channels=16),
      (2, 1, 28, 28)),

@@ -1,9 +1,8 @@
-set -x
-timeout 300 python -m pytest tests/test_parallel_gpu.py -q -m gpu 2>&1 | tail -3
-run() { PG_NCCL_MAX_CTAS=$1 PG_DP_RESERVE_SMS=$2 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 2 --steps 10 --warmup 3 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('ctas=$1 reserve=$2', d['value'], d['ms_per_step'], d['roofline']['achieved'], d['e2e']['value'])"; }
-run 0 0
-run 4 0
-run 4 4
-run 8 8
-run 2 2
+# data-parallel experiments (run under gpurun --gpus N, NG=N): NCCL CTA cap x reserved SMs x bucket granularity
+run() { PG_NCCL_MAX_CTAS=$1 PG_DP_RESERVE_SMS=$2 PG_DP_BUCKET_BLOCKS=$3 PG_DP_OVERLAP=$4 python -m torch.distributed.run --nnodes=1 --nproc-per-node ${NG:-2} --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus ${NG:-2} --steps 10 --warmup 3 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('ctas=$1 reserve=$2 bucket_blocks=$3 overlap=$4:', d['value'], 'img/s', d['ms_per_step'], 'ms  GEMM', d['roofline']['achieved'], 'TF  e2e', d['e2e']['value'])"; }
+run 0 0 1 1
+run 0 0 4 1
+run 0 0 24 1
+run 0 0 1 0
+run 8 8 6 1
 python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('1 gpu', d['value'], d['ms_per_step'], d['roofline']['achieved'])"
