@@ -8,12 +8,14 @@ encode pad + crop (no padded rows are ever computed), contracted on the tensor c
 
 import os
 
+import torch
 from torch import nn
 
 from .. import _lib as L
 from .. import nn as pg_nn
+from .. import ops
 from ..nn import pm
-from . import base
+from . import base, incremental
 
 RELU, TANH, NONE = L.ACT_RELU, L.ACT_TANH, L.ACT_NONE
 
@@ -82,8 +84,9 @@ class GatedPixelCNNLayer(nn.Module):
         return vstack, hstack, skip
 
 
-class GatedPixelCNN(base.AutoregressiveModel):
-    """The Gated PixelCNN model — constructor of reference gated_pixel_cnn.py:136-183."""
+class GatedPixelCNN(incremental.IncrementalSamplingMixin, base.AutoregressiveModel):
+    """The Gated PixelCNN model — constructor of reference gated_pixel_cnn.py:136-183.  `sample()` evaluates one pixel at a
+    time on line buffers (models/incremental.py) instead of one full forward per pixel."""
 
     def __init__(self, in_channels=1, out_channels=1, n_gated=10, gated_channels=128, head_channels=32, sample_fn=None):
         super().__init__(sample_fn)
@@ -99,6 +102,95 @@ class GatedPixelCNN(base.AutoregressiveModel):
             nn.ReLU(),
             pg_nn.TapConv2d(in_channels=head_channels, out_channels=out_channels, kernel_size=1),
         )
+
+    # ---- per-pixel program of the incremental sampler ----
+    # The horizontal stack of pixel p is evaluated when p's logits are needed.  The vertical stack's OUTPUT at p also sees
+    # image[p] (through `_vstack_1x1`; it only ever reaches pixels of later rows), so it is finished one step later, at
+    # the start of the program of p + 1, from the `Nx1(1xN(.))` value saved at p.  `1xN` outputs are not cached: the
+    # (k // 2 + 1) rows `Nx1` needs are recomputed from the layer's cached input (they are rows above p: complete).
+    def _layers(self):
+        return [self._input, *self._gated_layers]
+
+    def _incremental_ok(self, canvas):
+        c = self._input._out_channels
+        head = self._head[1].weight.shape[0]
+        return (super()._incremental_ok(canvas) and c % 8 == 0 and head % 8 == 0
+                and all(l._out_channels == c for l in self._gated_layers))
+
+    def _build_pixel_state(self, sp, c):
+        C, c_p = self._input._out_channels, ops.round_up(c, 8)
+        layers = self._layers()
+        image = sp.cache(c_p)
+        vc = [sp.cache(C) for _ in layers[:-1]]
+        hc = [sp.cache(C) for _ in layers[:-1]]
+        v2s = [torch.zeros(sp.n, 2 * C, dtype=torch.float32, device=sp.device) for _ in layers]
+        sp.prev = torch.zeros(1, dtype=torch.int64, device=sp.device)  # max(p - 1, 0): the pixel whose vertical stack is finished
+        rows = torch.arange(sp.S) // sp.w
+        valid = []
+        for layer in layers:  # [S, R] 1 / 0: is row (r + i - pad - 1) of the 1xN output inside the image (else: zero padding)
+            r_taps = layer._kernel_size // 2 + 1
+            ok = (rows.view(-1, 1) + torch.arange(r_taps).view(1, -1) - layer._padding - 1) >= 0
+            valid.append(ok.to(torch.bfloat16).to(sp.device))
+        return dict(image=image, vc=vc, hc=hc, v2s=v2s, valid=valid, caches=[image, *vc, *hc, *v2s], weights={}, c=c)
+
+    def _pack_pixel_weights(self):
+        w = {}
+        for i, layer in enumerate(self._layers()):
+            cin = layer._in_channels
+            cin_p = ops.round_up(cin, 8)
+            k, r_taps = layer._kernel_size, layer._kernel_size // 2 + 1
+            w[f"{i}v1"] = incremental.pack_taps(layer._vstack_1xN.weight, [(0, j, 0, 0) for j in range(k)], cin_p)
+            w[f"{i}v2"] = incremental.pack_taps(layer._vstack_Nx1.weight, [(ii, 0, 0, 0) for ii in range(r_taps)],
+                                                layer._out_channels)
+            w[f"{i}vx"] = incremental.pack_taps(layer._vstack_1x1.weight, [(0, 0, 0, 0)], cin_p)
+            w[f"{i}ln"] = ops.pack_weight(layer._link.weight)
+            w[f"{i}h"] = incremental.pack_taps(layer._hstack_1xN.weight, [(0, j, 0, 0) for j in range(r_taps)], cin_p)
+            w[f"{i}hr"] = ops.pack_weight(layer._hstack_residual.weight)
+            w[f"{i}hs"] = ops.pack_weight(layer._hstack_skip.weight)
+            for key, conv in (("v1", layer._vstack_1xN), ("v2", layer._vstack_Nx1), ("vx", layer._vstack_1x1),
+                              ("ln", layer._link), ("h", layer._hstack_1xN), ("hr", layer._hstack_residual),
+                              ("hs", layer._hstack_skip)):
+                w[f"{i}{key}b"] = conv.bias.detach().clone()
+        w["h1"], w["h1b"] = ops.pack_weight(self._head[1].weight), self._head[1].bias.detach().clone()
+        w["h3"], w["h3b"] = ops.pack_weight(self._head[3].weight), self._head[3].bias.detach().clone()
+        return w
+
+    def _before_pixel(self, sp, st, canvas, row, col):
+        sp.prev.fill_(max(row * canvas.shape[3] + col - 1, 0))
+
+    def _pixel_program(self, sp, st):
+        W, n = st["weights"], sp.n
+        layers = self._layers()
+        last = len(layers) - 1
+        # (1) the previous pixel is final now: finish its vertical-stack outputs
+        vin = st["image"].index_select(1, sp.prev)[:, 0]
+        for i in range(last):
+            vv = sp.linear(vin, W[f"{i}vx"], W[f"{i}vxb"], res0=st["v2s"][i])
+            vin = pm.gated(vv, TANH)
+            st["vc"][i].index_copy_(1, sp.prev, vin.unsqueeze(1))
+        # (2) position p
+        h_f = skips = None
+        for i, layer in enumerate(layers):
+            k, pd, mc = layer._kernel_size, layer._padding, int(layer._mask_center)
+            r_taps, C = k // 2 + 1, layer._out_channels
+            v_src = st["image"] if i == 0 else st["vc"][i - 1]
+            h_src = st["image"] if i == 0 else st["hc"][i - 1]
+            offs_v = [(ii - pd - 1, j - pd) for ii in range(r_taps) for j in range(k)]
+            a = sp.gather(v_src, offs_v).view(n * r_taps, -1)
+            v1 = sp.linear(a, W[f"{i}v1"], W[f"{i}v1b"]).view(n, r_taps, C)
+            v1 = v1 * st["valid"][i].index_select(0, sp.pos).view(1, r_taps, 1)   # rows above the image are zero padding
+            v2_b, _, v2_f = ops.linear_fwd(v1.view(n, r_taps * C), W[f"{i}v2"], W[f"{i}v2b"], want_f32=True, skinny=True)
+            st["v2s"][i].copy_(v2_f)
+            link = sp.linear(v2_b, W[f"{i}ln"], W[f"{i}lnb"], f32=True)
+            offs_h = [(0, j - pd - mc) for j in range(r_taps)]
+            hh = sp.linear(sp.gather(h_src, offs_h), W[f"{i}h"], W[f"{i}hb"], res0=link)
+            hs = pm.gated(hh, TANH)
+            skips = sp.linear(hs, W[f"{i}hs"], W[f"{i}hsb"], res0=skips, f32=True)
+            h_b, _, h_f = ops.linear_fwd(hs, W[f"{i}hr"], W[f"{i}hrb"], res0=None if mc else h_f, want_f32=True, skinny=True)
+            if i < last:
+                sp.write(st["hc"][i], h_b)
+        t = sp.linear(sp.act(skips, RELU), W["h1"], W["h1b"], act=RELU)
+        return sp.linear(t, W["h3"], W["h3b"], f32=True)
 
     def _forward_pm(self, x):
         """The whole network on pixel-major tensors: NCHW only at the image and at the logits."""

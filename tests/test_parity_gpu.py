@@ -306,6 +306,9 @@ def test_sampling_follows_reference_raster_order(pg, name):
     ("PixelCNN", dict(in_channels=3, out_channels=3, n_residual=2, residual_channels=32, head_channels=16), (2, 3, 8, 16)),
     ("PixelSNAIL", dict(in_channels=3, out_channels=3, n_channels=64, n_pixel_snail_blocks=2, n_residual_blocks=2,
                         attention_key_channels=16, attention_value_channels=32), (2, 3, 16, 16)),
+    ("GatedPixelCNN", dict(in_channels=1, out_channels=1, n_gated=3, gated_channels=32, head_channels=16), (3, 1, 28, 28)),
+    ("GatedPixelCNN", dict(in_channels=3, out_channels=3, n_gated=2, gated_channels=64, head_channels=32), (2, 3, 8, 16)),
+    ("GatedPixelCNN", dict(in_channels=1, out_channels=1, n_gated=0, gated_channels=16, head_channels=8), (2, 1, 6, 5)),
     ("PixelSNAIL", dict(in_channels=1, out_channels=1, n_channels=32, n_pixel_snail_blocks=1, n_residual_blocks=1,
                         attention_key_channels=4, attention_value_channels=128), (4, 1, 28, 28)),
 ])

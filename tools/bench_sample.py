@@ -8,6 +8,7 @@ from pytorch_generative_b200 import models
 dev = torch.device("cuda:0")
 CASES = {
     "c1": (lambda: models.PixelCNN(1, 1, 15, 16, 32), (1, 28, 28)),
+    "c3": (lambda: models.GatedPixelCNN(3, 3, 15, 128, 32), (3, 32, 32)),
     "c4": (lambda: models.PixelSNAIL(3, 3, 256, 8, 2, 16, 128), (3, 32, 32)),
     "c5": (lambda: models.ImageGPT(3, 3, 32, 24, 8, 512), (3, 32, 32)),
 }
