@@ -158,7 +158,13 @@ class _ImageGPTStack(torch.autograd.Function):
         # data parallelism: each block's slice of the arena is handed to the bucket hook (an asynchronous all-reduce)
         # as soon as its last wgrad GEMM is queued; see parallel.OverlappedGradAverager
         bucket_hook = sv["hook"] if _arena_views_are_grads(sv) else None
-        bucket_blocks = max(1, int(os.environ.get("PG_DP_BUCKET_BLOCKS", "1")))  # transformer blocks per all-reduce
+        # transformer blocks per all-reduce; 0 = the whole stack in one bucket, issued when block 0's last wgrad is queued
+        # (overlaps the input convolution's backward and the small-gradient bucket only).  Finer buckets overlap more but
+        # every NCCL kernel that runs next to the GEMMs slows them by more than it hides: 8 x B200, 24 / 6 / 1 blocks per
+        # bucket = 8000 / 7855 / 7637 img/s (profiles/r02_bench_multigpu.txt).
+        bucket_blocks = int(os.environ.get("PG_DP_BUCKET_BLOCKS", "0"))
+        if bucket_blocks <= 0:
+            bucket_blocks = n_blocks
         pending = []
 
         for b in reversed(range(n_blocks)):
