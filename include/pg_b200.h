@@ -45,6 +45,9 @@ enum { PG_ACT_NONE = 0, PG_ACT_RELU = 1, PG_ACT_GELU = 2, PG_ACT_ELU = 3, PG_ACT
 /* OR-ed into pg_gemm_epilogue.act: out_pre receives act'(pre) instead of pre, so that the matching dgrad epilogue
  * (dact = PG_ACT_GIVEN) is a single multiply. */
 #define PG_ACT_STORE_DERIV 0x100
+/* OR-ed into pg_gemm_epilogue.act: res0 / res1 point to bf16 [M,N] matrices (pitch ld_res in bf16 elements, a multiple of 8)
+ * instead of fp32 ones — short-lived sums (GatedPixelCNN's vertical-to-horizontal link) that are not a residual stream. */
+#define PG_ACT_RES_BF16 0x200
 
 /* ---------------------------------------------------------------------------------------------
  * Channel contraction (every nn.Conv2d 1x1 on the path and, per live tap, every masked conv):

@@ -23,6 +23,7 @@ ACT_GIVEN = 5  # dact only: aux already holds the derivative
 ACT_RELU_OUT, ACT_ELU_OUT = 6, 7  # dact only: aux holds the activated value
 DACT_FROM_OUT = {ACT_RELU: ACT_RELU_OUT, ACT_ELU: ACT_ELU_OUT}
 ACT_STORE_DERIV = 0x100  # OR-ed into act: out_pre receives act'(pre)
+ACT_RES_BF16 = 0x200  # OR-ed into act: res0 / res1 are bf16 matrices (set by _epilogue from the tensors' dtype)
 ACT_BY_NAME = {None: ACT_NONE, "none": ACT_NONE, "relu": ACT_RELU, "gelu": ACT_GELU, "elu": ACT_ELU, "tanh": ACT_TANH}
 
 _vp, _i32, _i64, _f32 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float
@@ -218,7 +219,7 @@ def gemm(A, B, M, N, K, *, a_mn=False, b_mn=False, bias=None, aux=None, dact=ACT
 def _gemm_io(M, N, K, out_bf16, out_pre, out_f32, aux, res0, res1):
     """Algorithmic HBM bytes of one contraction: both operands once, every epilogue tensor once."""
     return 2 * (M * K + N * K) + M * N * (2 * (out_bf16 is not None) + 2 * (out_pre is not None) + 4 * (out_f32 is not None)
-                                          + 2 * (aux is not None) + 4 * (res0 is not None) + 4 * (res1 is not None))
+                                          + 2 * (aux is not None) + sum(r.element_size() for r in (res0, res1) if r is not None))
 
 
 @_device_guarded
@@ -262,14 +263,17 @@ def _epilogue(M, N, bias, aux, dact, res0, res1, out_bf16, out_pre, out_f32, act
     e.bias = _ptr(bias)
     if bias is not None:
         assert bias.dtype == torch.float32 and bias.numel() >= N and bias.is_contiguous()
-    ld_res = 0
+    ld_res, res_dtype = 0, None
     for r in (res0, res1):
         if r is not None:
-            assert r.dtype == torch.float32 and r.shape[0] >= M
+            assert r.dtype in (torch.float32, torch.bfloat16) and r.shape[0] >= M
+            assert res_dtype in (None, r.dtype), "res0/res1 must share a dtype"
             p, ld = _pm(r)
             assert ld_res in (0, ld), "res0/res1 must share a pitch"
-            ld_res = ld
+            ld_res, res_dtype = ld, r.dtype
     e.res0, e.res1, e.ld_res = _ptr(res0), _ptr(res1), ld_res
+    if res_dtype == torch.bfloat16:
+        act = act | ACT_RES_BF16
     if aux is not None:
         assert aux.dtype == torch.bfloat16
         e.aux, e.ld_aux = _pm(aux)

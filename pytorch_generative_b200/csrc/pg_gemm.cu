@@ -57,6 +57,7 @@ struct GemmParams {
   // staged (TMA) epilogue plan
   int staged;
   int store_deriv;  // out_pre receives act'(pre) (PG_ACT_STORE_DERIV)
+  int res_bf16;     // res0 / res1 are bf16 matrices (PG_ACT_RES_BF16)
   int epi_depth;    // staging stages per epilogue warpgroup (1 or 2)
   int epi_stage_bytes;
   int off_res0, off_res1, off_aux, off_outf, off_outb, off_outp;  // slab offsets inside an epilogue stage, -1 = absent
@@ -67,6 +68,7 @@ struct GemmParams {
 // ------------------------------------------------------------------------------------------------
 // Direct epilogue (generic fallback): `acc` = 32 consecutive fp32 accumulator columns of output row `row`.
 // ------------------------------------------------------------------------------------------------
+template <bool BF16_RES = true>
 __device__ __forceinline__ void epilogue_row32(const GemmParams& p, int row, int col0, int ncols, bool first_split,
                                                const uint32_t (&acc)[32]) {
   const pg_gemm_epilogue& e = p.epi;
@@ -109,7 +111,10 @@ __device__ __forceinline__ void epilogue_row32(const GemmParams& p, int row, int
 #pragma unroll
   for (int which = 0; which < 2; ++which) {
     const float* rp = which == 0 ? e.res0 : e.res1;
-    if (first_split && rp) {
+    if (BF16_RES && first_split && rp && p.res_bf16) {
+      const bf16* r = reinterpret_cast<const bf16*>(rp) + (size_t)row * e.ld_res + col0;
+      for (int i = 0; i < ncols; ++i) v[i] += __bfloat162float(r[i]);
+    } else if (first_split && rp) {
       const float* r = rp + (size_t)row * e.ld_res + col0;
       if (full) {
 #pragma unroll
@@ -195,6 +200,20 @@ __device__ __forceinline__ void slab_bf16_load(const uint8_t* slab, int r, float
       const float2 f = unpack_bf16x2(ww[j]);
       x[8 * u + 2 * j] = f.x;
       x[8 * u + 2 * j + 1] = f.y;
+    }
+  }
+}
+__device__ __forceinline__ void slab_bf16_add(const uint8_t* slab, int r, float (&v)[32]) {
+  const uint8_t* row = slab + r * 64;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const uint4 w = *reinterpret_cast<const uint4*>(row + ((u ^ ((r >> 1) & 3)) << 4));
+    const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = unpack_bf16x2(ww[j]);
+      v[8 * u + 2 * j] += f.x;
+      v[8 * u + 2 * j + 1] += f.y;
     }
   }
 }
@@ -466,7 +485,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * BN + c * 32, acc);
         tmem_wait_ld();
         if (!p.staged) {
-          if (row < p.M && col0 < p.N) epilogue_row32(p, row, col0, min(32, p.N - col0), ks == 0, acc);
+          if (row < p.M && col0 < p.N) epilogue_row32<(EPI_GROUPS < 3)>(p, row, col0, min(32, p.N - col0), ks == 0, acc);
           continue;
         }
         float v[32];
@@ -502,8 +521,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int i = 0; i < 32; ++i) v[i] *= pg_act_bwd(e.dact, x[i]);
           }
         }
-        if (p.off_res0 >= 0) slab_f32_add(base + p.off_res0, r, v);
-        if (p.off_res1 >= 0) slab_f32_add(base + p.off_res1, r, v);
+        if (EPI_GROUPS < 3 && p.res_bf16) {  // (the register-tight three-group build never sees bf16 residuals: dispatch_bn)
+          if (p.off_res0 >= 0) slab_bf16_add(base + p.off_res0, r, v);
+          if (p.off_res1 >= 0) slab_bf16_add(base + p.off_res1, r, v);
+        } else {
+          if (p.off_res0 >= 0) slab_f32_add(base + p.off_res0, r, v);
+          if (p.off_res1 >= 0) slab_f32_add(base + p.off_res1, r, v);
+        }
         // the TMA store that last used this stage's output slabs must have finished reading them
         if (leader) {
           if (depth > 1) tma_store_wait_read<1>();
@@ -665,8 +689,13 @@ gemm_skinny_kernel(const bf16* __restrict__ A, int64_t lda, const bf16* __restri
     const int m = lane;
     float t = mine * e.alpha;
     if (e.bias) t += e.bias[n];
-    if (e.res0) t += e.res0[(size_t)m * e.ld_res + n];
-    if (e.res1) t += e.res1[(size_t)m * e.ld_res + n];
+    if (p.res_bf16) {
+      if (e.res0) t += __bfloat162float(reinterpret_cast<const bf16*>(e.res0)[(size_t)m * e.ld_res + n]);
+      if (e.res1) t += __bfloat162float(reinterpret_cast<const bf16*>(e.res1)[(size_t)m * e.ld_res + n]);
+    } else {
+      if (e.res0) t += e.res0[(size_t)m * e.ld_res + n];
+      if (e.res1) t += e.res1[(size_t)m * e.ld_res + n];
+    }
     if (e.out_f32) e.out_f32[(size_t)m * e.ld_out_f32 + n] = t;
     if (e.out_pre)
       reinterpret_cast<bf16*>(e.out_pre)[(size_t)m * e.ld_out_pre + n] =
@@ -720,15 +749,17 @@ int launch_tc(const void* A, int64_t lda, const void* B, int64_t ldb, GemmParams
   if (p.staged) {
     int off = 0;
     auto add = [&](int& slot, int bytes) { slot = off; off += bytes; };
-    if (e.res0) { add(p.off_res0, SLAB_F32); p.in_bytes += SLAB_F32; }
-    if (e.res1) { add(p.off_res1, SLAB_F32); p.in_bytes += SLAB_F32; }
+    const int slab_res = p.res_bf16 ? SLAB_BF16 : SLAB_F32;
+    if (e.res0) { add(p.off_res0, slab_res); p.in_bytes += slab_res; }
+    if (e.res1) { add(p.off_res1, slab_res); p.in_bytes += slab_res; }
     if (e.dact != PG_ACT_NONE) { add(p.off_aux, SLAB_BF16); p.in_bytes += SLAB_BF16; }
     if (e.out_f32) add(p.off_outf, SLAB_F32);
     if (e.out_pre) add(p.off_outp, SLAB_BF16);
     if (e.out_bf16) add(p.off_outb, SLAB_BF16);
     p.epi_stage_bytes = off;
-    if (e.res0 && pg_make_tmap_2d(&em.res0, e.res0, 4, p.M, p.N, e.ld_res, BM, 32, 128)) return 1;
-    if (e.res1 && pg_make_tmap_2d(&em.res1, e.res1, 4, p.M, p.N, e.ld_res, BM, 32, 128)) return 1;
+    const int res_es = p.res_bf16 ? 2 : 4, res_sw = p.res_bf16 ? 64 : 128;
+    if (e.res0 && pg_make_tmap_2d(&em.res0, e.res0, res_es, p.M, p.N, e.ld_res, BM, 32, res_sw)) return 1;
+    if (e.res1 && pg_make_tmap_2d(&em.res1, e.res1, res_es, p.M, p.N, e.ld_res, BM, 32, res_sw)) return 1;
     if (e.dact != PG_ACT_NONE && pg_make_tmap_2d(&em.aux, e.aux, 2, p.M, p.N, e.ld_aux, BM, 32, 64)) return 1;
     if (e.out_f32 && pg_make_tmap_2d(&em.out_f32, e.out_f32, 4, p.M, p.N, e.ld_out_f32, BM, 32, 128)) return 1;
     if (e.out_pre && pg_make_tmap_2d(&em.out_pre, e.out_pre, 2, p.M, p.N, e.ld_out_pre, BM, 32, 64)) return 1;
@@ -784,7 +815,8 @@ int dispatch_bn(const void* A, int64_t lda, const void* B, int64_t ldb, GemmPara
   if (B_MN && bn < 64) bn = 64;  // MN-major operands are staged in 64-wide swizzle atoms
   if (p.conv.mode == 2) bn = (p.conv.C % 256 == 0) ? 256 : (p.conv.C % 128 == 0) ? 128 : 64;  // taps are whole N blocks
   const pg_gemm_epilogue& e = p.epi;
-  const int epi = (e.res0 ? SLAB_F32 : 0) + (e.res1 ? SLAB_F32 : 0) + (e.dact != PG_ACT_NONE ? SLAB_BF16 : 0) +
+  const int slab_res = p.res_bf16 ? SLAB_BF16 : SLAB_F32;
+  const int epi = (e.res0 ? slab_res : 0) + (e.res1 ? slab_res : 0) + (e.dact != PG_ACT_NONE ? SLAB_BF16 : 0) +
                   (e.out_f32 ? SLAB_F32 : 0) + (e.out_pre ? SLAB_BF16 : 0) + (e.out_bf16 ? SLAB_BF16 : 0);
   const bool pure_acc = e.accumulate && !e.bias && !e.res0 && !e.res1;
   const bool staged = p.vec_ok && (!e.accumulate || pure_acc);
@@ -800,7 +832,7 @@ int dispatch_bn(const void* A, int64_t lda, const void* B, int64_t ldb, GemmPara
       // Short-K tiles (K <= 1024) spend most of their time in the epilogue: a third epilogue warpgroup hides more
       // of its latency, provided its two extra staging stages still leave a 3-deep operand pipeline.
       static const bool no_g3 = getenv("PG_GEMM_NO_G3") != nullptr;
-      if (!no_g3 && staged && p.k_iters <= 16 && (SMEM_LIMIT - 6 * epi - 1536) / PAIR_STAGE >= 3)
+      if (!no_g3 && staged && !p.res_bf16 && p.k_iters <= 16 && (SMEM_LIMIT - 6 * epi - 1536) / PAIR_STAGE >= 3)
         return launch_tc<256, false, B_MN, true, 3>(A, lda, B, ldb, p, stream);
       return launch_tc<256, false, B_MN, true>(A, lda, B, ldb, p, stream);
     }
@@ -848,14 +880,16 @@ static int gemm_entry(const void* A, int a_mn_major, int64_t lda, const void* B,
   p.splits = (p.k_iters + p.k_per_split - 1) / p.k_per_split;  // no empty split
   p.epi = *epi;
   p.store_deriv = (epi->act & PG_ACT_STORE_DERIV) ? 1 : 0;
+  p.res_bf16 = (epi->act & PG_ACT_RES_BF16) ? 1 : 0;
   p.epi.act = epi->act & 0xff;
   PG_REQUIRE(!p.store_deriv || epi->out_pre, "pg_gemm_bf16: PG_ACT_STORE_DERIV needs out_pre");
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   p.vec_ok = 1;
   if (epi->bias && !al16(epi->bias)) p.vec_ok = 0;
   if (epi->aux && (!al16(epi->aux) || epi->ld_aux % 8)) p.vec_ok = 0;
-  if (epi->res0 && (!al16(epi->res0) || epi->ld_res % 4)) p.vec_ok = 0;
-  if (epi->res1 && (!al16(epi->res1) || epi->ld_res % 4)) p.vec_ok = 0;
+  const int res_mult = p.res_bf16 ? 8 : 4;
+  if (epi->res0 && (!al16(epi->res0) || epi->ld_res % res_mult)) p.vec_ok = 0;
+  if (epi->res1 && (!al16(epi->res1) || epi->ld_res % res_mult)) p.vec_ok = 0;
   if (epi->out_f32 && (!al16(epi->out_f32) || epi->ld_out_f32 % 4)) p.vec_ok = 0;
   if (epi->out_pre && (!al16(epi->out_pre) || epi->ld_out_pre % 8)) p.vec_ok = 0;
   if (epi->out_bf16 && (!al16(epi->out_bf16) || epi->ld_out_bf16 % 8)) p.vec_ok = 0;

@@ -56,13 +56,15 @@ class GatedPixelCNNLayer(nn.Module):
             v1 = pm.act_cast(pm.small_conv(image, self._vstack_1xN.weight, self._vstack_1xN.bias, (0, p)))
         else:
             v1, _ = pm.conv(v_b, self._vstack_1xN.weight, self._vstack_1xN.bias, geom, (0, p))
-        v2_f, v2_b = pm.conv(v1, self._vstack_Nx1.weight, self._vstack_Nx1.bias, geom, (p + 1, 0), emit=NONE, out_f32=True)
-        link, _ = pm.conv(v2_f, self._link.weight, self._link.bias, geom, xa=v2_b, out_f32=True)
+        # Nx1(1xN(.)) and the link are short-lived sums, not streams: bf16 tensors, added in the consumer's epilogue as
+        # bf16 residuals, so their gradients (the gate's bf16 output gradients) flow back without an fp32 round trip
+        v2, _ = pm.conv(v1, self._vstack_Nx1.weight, self._vstack_Nx1.bias, geom, (p + 1, 0))
+        link, _ = pm.conv(v2, self._link.weight, self._link.bias, geom)
         if image is not None:
-            vv = v2_f + pm.small_conv(image, self._vstack_1x1.weight, self._vstack_1x1.bias, (0, 0))
+            vv = v2 + pm.small_conv(image, self._vstack_1x1.weight, self._vstack_1x1.bias, (0, 0))
             hh = link + pm.small_conv(image, self._hstack_1xN.weight, self._hstack_1xN.bias, (0, p + int(self._mask_center)))
         else:
-            vv, _ = pm.conv(v_b, self._vstack_1x1.weight, self._vstack_1x1.bias, geom, res=v2_f)
+            vv, _ = pm.conv(v_b, self._vstack_1x1.weight, self._vstack_1x1.bias, geom, res=v2)
             hh, _ = pm.conv(h_f, self._hstack_1xN.weight, self._hstack_1xN.bias, geom, (0, p + int(self._mask_center)),
                             xa=h_b, res=link)
         v_out = pm.gated(vv, TANH)
@@ -123,7 +125,7 @@ class GatedPixelCNN(incremental.IncrementalSamplingMixin, base.AutoregressiveMod
         image = sp.cache(c_p)
         vc = [sp.cache(C) for _ in layers[:-1]]
         hc = [sp.cache(C) for _ in layers[:-1]]
-        v2s = [torch.zeros(sp.n, 2 * C, dtype=torch.float32, device=sp.device) for _ in layers]
+        v2s = [torch.zeros(sp.n, 2 * C, dtype=torch.bfloat16, device=sp.device) for _ in layers]
         sp.prev = torch.zeros(1, dtype=torch.int64, device=sp.device)  # max(p - 1, 0): the pixel whose vertical stack is finished
         rows = torch.arange(sp.S) // sp.w
         valid = []
@@ -179,9 +181,9 @@ class GatedPixelCNN(incremental.IncrementalSamplingMixin, base.AutoregressiveMod
             a = sp.gather(v_src, offs_v).view(n * r_taps, -1)
             v1 = sp.linear(a, W[f"{i}v1"], W[f"{i}v1b"]).view(n, r_taps, C)
             v1 = v1 * st["valid"][i].index_select(0, sp.pos).view(1, r_taps, 1)   # rows above the image are zero padding
-            v2_b, _, v2_f = ops.linear_fwd(v1.view(n, r_taps * C), W[f"{i}v2"], W[f"{i}v2b"], want_f32=True, skinny=True)
-            st["v2s"][i].copy_(v2_f)
-            link = sp.linear(v2_b, W[f"{i}ln"], W[f"{i}lnb"], f32=True)
+            v2 = sp.linear(v1.view(n, r_taps * C), W[f"{i}v2"], W[f"{i}v2b"])
+            st["v2s"][i].copy_(v2)
+            link = sp.linear(v2, W[f"{i}ln"], W[f"{i}lnb"])
             offs_h = [(0, j - pd - mc) for j in range(r_taps)]
             hh = sp.linear(sp.gather(h_src, offs_h), W[f"{i}h"], W[f"{i}hb"], res0=link)
             hs = pm.gated(hh, TANH)

@@ -212,7 +212,8 @@ class _Conv(torch.autograd.Function):
         # backward needs the operand itself (wgrad); the activated input also yields in_act' (dgrad epilogue), the
         # activated output yields emit' when it is a true post-activation output
         ctx.save_for_backward(xa, wcat, ya if (want_act and emit_mode == POST and emit != L.ACT_NONE) else None)
-        ctx.meta = (geom, taps, pointwise, in_act, weight.shape, bias is not None, res is not None, x.dtype, emit, emit_mode)
+        ctx.meta = (geom, taps, pointwise, in_act, weight.shape, bias is not None, None if res is None else res.dtype,
+                    x.dtype, emit, emit_mode)
         y = (yf if out_f32 else yb) if want_main else None
         if ya is not None and emit_mode == COMPANION:
             ctx.mark_non_differentiable(ya)
@@ -221,7 +222,7 @@ class _Conv(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy, dya):
         xa, wcat, ya = ctx.saved_tensors
-        geom, taps, pointwise, in_act, wshape, has_bias, has_res, x_dtype, emit, emit_mode = ctx.meta
+        geom, taps, pointwise, in_act, wshape, has_bias, res_dtype, x_dtype, emit, emit_mode = ctx.meta
         cout, cin, kh, kw = wshape
         cin_p = xa.shape[1]
         cout_p = ops.round_up(cout, 8)
@@ -265,7 +266,9 @@ class _Conv(torch.autograd.Function):
                 dxb, dxf = ops.conv_dgrad(dyb, wcat, cin_p, geom.n, geom.h, geom.w, taps, aux=aux, dact=dact,
                                           want_f32=want_f32, want_bf16=not want_f32)
                 dx = dxf if want_f32 else dxb
-        dres = (dy if dy.dtype == F32 else dy.float()) if has_res else None
+        dres = None
+        if res_dtype is not None:  # d(res) = dy: hand over the copy that already has the residual's dtype
+            dres = dy if dy.dtype == res_dtype else (dyb if (res_dtype == BF16 and cout_p == cout) else dy.to(res_dtype))
         return dx, None, dw, db, dres, None, None, None, None, None, None, None
 
 
@@ -277,7 +280,8 @@ def conv(x, weight, bias, geom, padding=(0, 0), *, in_act=L.ACT_NONE, xa=None, r
     in_act   activation the reference applies in front of this conv (ReLU / ELU / none); its derivative is applied by
              this conv's dgrad epilogue, so the gradient this op returns for x is w.r.t. the PRE-activation value;
     xa       bf16(in_act(x)) if a producer epilogue already emitted it (else built here with one elementwise pass);
-    res      optional fp32 [P, Cout] added to the output in the epilogue (residual / skip / link sums);
+    res      optional [P, Cout] added to the output in the epilogue: fp32 (a residual / skip stream) or bf16 (a short-lived
+             sum such as GatedPixelCNN's vertical-to-horizontal link; its gradient then stays bf16 as well);
     emit     activation id (or ACT_NONE for a plain bf16 copy) of a second, bf16 output produced by the same epilogue;
     emit_mode COMPANION: `ya` is a non-differentiable operand copy of y (pass it as `xa` to the consumers of y);
              PRE_GRAD: `ya` stands for y in the graph and may only feed `conv(ya, in_act=emit, xa=ya)`, whose fused
@@ -287,7 +291,5 @@ def conv(x, weight, bias, geom, padding=(0, 0), *, in_act=L.ACT_NONE, xa=None, r
     Returns (y, ya)."""
     if xa is None:
         xa = act_cast(x, in_act) if (in_act != L.ACT_NONE or x.dtype != BF16) else x
-    if res is not None:
-        assert res.dtype == F32, "residual sums live in fp32"
     return _Conv.apply(x, xa.detach() if xa is not x else xa, weight, bias, res, geom, tuple(padding), in_act, emit, emit_mode,
                        out_f32, want_main)

@@ -144,6 +144,34 @@ def test_gemm_epilogue_forward(L, shape, impl):
     assert_close("gelu bf16", out_b[:, :N], _gelu(pre), rtol=2 ** -8)
 
 
+@pytest.mark.parametrize("impl", [0, 1, 2])
+@pytest.mark.parametrize("shape", [(512, 256, 512), (19200, 256, 128), (1000, 200, 72), (16, 256, 384)])
+def test_gemm_bf16_residuals(L, shape, impl):
+    """PG_ACT_RES_BF16: res0 / res1 are bf16 matrices (GatedPixelCNN's vertical-to-horizontal sums) — tcgen05 kernel
+    (single CTA and CTA pairs, staged and direct epilogues), SIMT cross-check and skinny kernel."""
+    M, N, K = shape
+    if (impl == 2) != (M <= 32):
+        pytest.skip("the skinny kernel takes M <= 32 only")
+    A, B, acc = _operands(M, N, K, False, False, seed=31)
+    g = torch.Generator(device="cpu").manual_seed(32)
+    bias = torch.randn(N, generator=g).to(_dev())
+    Np = (N + 7) // 8 * 8
+    r0 = torch.randn(M, Np, generator=g).to(_dev()).bfloat16()
+    r1 = torch.randn(M, Np, generator=g).to(_dev()).bfloat16()
+    out_f = torch.empty(M, Np, device=_dev())
+    out_b = torch.empty(M, Np, device=_dev(), dtype=torch.bfloat16)
+    L.gemm(A, B, M, N, K, bias=bias, res0=r0[:, :N], res1=r1[:, :N], out_f32=out_f[:, :N], out_bf16=out_b[:, :N],
+           act=L.ACT_RELU, impl=impl)
+    torch.cuda.synchronize()
+    pre = acc + bias + r0[:, :N].float() + r1[:, :N].float()
+    assert_close("pre fp32", out_f[:, :N], pre, rtol=2e-5, atol=1e-4)
+    assert_close("relu bf16", out_b[:, :N], torch.relu(pre), rtol=2 ** -8)
+    out_1 = torch.empty(M, Np, device=_dev(), dtype=torch.bfloat16)
+    L.gemm(A, B, M, N, K, res0=r1[:, :N], out_bf16=out_1[:, :N], impl=impl)
+    torch.cuda.synchronize()
+    assert_close("one bf16 residual", out_1[:, :N], acc + r1[:, :N].float(), rtol=2 ** -8)
+
+
 @pytest.mark.parametrize("impl", [0, 1])
 @pytest.mark.parametrize("M", [640, 19200])
 def test_gemm_epilogue_dact(L, impl, M):
