@@ -211,6 +211,9 @@ class _Conv(torch.autograd.Function):
             ya, yb, yf = ops.conv_fwd(xa, wcat, b, geom.n, geom.h, geom.w, taps, **kw_out)
         # backward needs the operand itself (wgrad); the activated input also yields in_act' (dgrad epilogue), the
         # activated output yields emit' when it is a true post-activation output
+        # undefined output gradients arrive as None, not as zero tensors: the companion output is never differentiated, and
+        # a materialised zero gradient for it costs a fill, a dtype conversion and an add per layer
+        ctx.set_materialize_grads(False)
         ctx.save_for_backward(xa, wcat, ya if (want_act and emit_mode == POST and emit != L.ACT_NONE) else None)
         ctx.meta = (geom, taps, pointwise, in_act, weight.shape, bias is not None, None if res is None else res.dtype,
                     x.dtype, emit, emit_mode)
@@ -227,6 +230,10 @@ class _Conv(torch.autograd.Function):
         cin_p = xa.shape[1]
         cout_p = ops.round_up(cout, 8)
         T = len(taps)
+        if dy is None and dya is None:  # nothing downstream used this convolution
+            return (None,) * 12
+        if emit_mode == COMPANION:
+            dya = None
         if dya is not None and emit_mode == POST and emit != L.ACT_NONE:
             # gradient w.r.t. the activated output: back through emit (relu / elu) from the activated value itself
             d = torch.empty(ya.shape, dtype=BF16, device=ya.device)
