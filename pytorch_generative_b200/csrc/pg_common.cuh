@@ -520,6 +520,13 @@ __device__ __forceinline__ float pg_exp2_fast(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// ELU for bf16 outputs (the GEMM epilogues): one MUFU; the cubic covers the cancellation range of e^x - 1
+// (|rel err| < 2e-5 everywhere, far inside bf16's 2^-9)
+__device__ __forceinline__ float pg_elu_fast(float x) {
+  const float e = pg_exp2_fast(x * 1.4426950408889634f) - 1.f;
+  const float p = x * fmaf(x, fmaf(x, 0.16666667f, 0.5f), 1.f);
+  return x > 0.f ? x : (x > -0.0625f ? p : e);
+}
 // atanh(erf(x / sqrt 2)) ~= x (c0 + c1 x^2 + c2 x^4): least-squares fit on [-8, 8] (tools: see DESIGN.md)
 __device__ __forceinline__ float pg_gelu_q(float x) {
   x = fminf(fmaxf(x, -8.f), 8.f);  // the fit is monotone on [-8, 8]; tanh is saturated there (q(8) = 13.7)

@@ -516,6 +516,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           } else if (e.dact == PG_ACT_GELU) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] *= pg_act_bwd(PG_ACT_GELU, x[i]);
+          } else if (e.dact == PG_ACT_ELU_OUT) {  // aux = elu(pre): elu' = 1 (a > 0) or a + 1
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] *= (x[i] > 0.f ? 1.f : x[i] + 1.f);
+          } else if (e.dact == PG_ACT_RELU_OUT || e.dact == PG_ACT_RELU) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = x[i] > 0.f ? v[i] : 0.f;
           } else {
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] *= pg_act_bwd(e.dact, x[i]);
@@ -561,6 +567,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             } else if (e.act == PG_ACT_RELU) {
 #pragma unroll
               for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+            } else if (e.act == PG_ACT_ELU) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = pg_elu_fast(v[i]);
             } else if (e.act != PG_ACT_NONE) {
 #pragma unroll
               for (int i = 0; i < 32; ++i) v[i] = pg_act_fwd(e.act, v[i]);

@@ -45,7 +45,42 @@ def case(label, n, h, w, cin, cout, kh, kw, pad):
         print(f"{label:34s} {name:30s} {ms * 1e3:8.1f} us  {gf / ms:8.1f} TFLOP/s", flush=True)
 
 
+def variants_c4():
+    """The epilogue variants the PixelSNAIL stack actually launches (nn/pm.py), at C4's shapes."""
+    n, h, w, C = 128, 32, 32, 256
+    P = n * h * w
+    taps = conv_taps(2, 2, 1, 1)
+    xa = torch.randn(P, C, device=dev).to(BF16)
+    t = torch.randn(P, C, device=dev).to(BF16)
+    w1 = (torch.randn(C, 4 * C, device=dev) * 0.05).to(BF16)
+    w2 = (torch.randn(2 * C, 4 * C, device=dev) * 0.05).to(BF16)
+    w11 = (torch.randn(C, C, device=dev) * 0.05).to(BF16)
+    b1, b2 = torch.zeros(C, device=dev), torch.zeros(2 * C, device=dev)
+    dy1 = torch.randn(P, C, device=dev).to(BF16)
+    dy2 = torch.randn(P, 2 * C, device=dev).to(BF16)
+    res = torch.randn(P, C, device=dev)
+    gf1, gf2, gf11 = 2.0 * P * C * 4 * C / 1e9, 2.0 * P * 2 * C * 4 * C / 1e9, 2.0 * P * C * C / 1e9
+    rows = [
+        ("2x2 conv1 fwd: elu out only", gf1, lambda: ops.conv_fwd(xa, w1, b1, n, h, w, taps, act=L.ACT_ELU)),
+        ("2x2 conv2 fwd: bf16 [P,512]", gf2, lambda: ops.conv_fwd(t, w2, b2, n, h, w, taps)),
+        ("2x2 conv2 dgrad: elu' from out, bf16", gf2, lambda: ops.conv_dgrad(dy2, w2, C, n, h, w, taps, aux=t, dact=L.ACT_ELU_OUT)),
+        ("2x2 conv1 dgrad: elu' from out, f32", gf1, lambda: ops.conv_dgrad(dy1, w1, C, n, h, w, taps, aux=xa, dact=L.ACT_ELU_OUT,
+                                                                       want_f32=True, want_bf16=False)),
+        ("2x2 conv1 dgrad: plain bf16", gf1, lambda: ops.conv_dgrad(dy1, w1, C, n, h, w, taps)),
+        ("1x1 fwd: elu out only", gf11, lambda: ops.linear_fwd(xa, w11, b1, act=L.ACT_ELU)),
+        ("1x1 fwd: f32 + res", gf11, lambda: ops.linear_fwd(xa, w11, b1, res0=res, want_bf16=False, want_f32=True)),
+        ("1x1 dgrad: elu' from out, f32", gf11, lambda: ops.linear_dgrad(dy1, w11, aux=xa, dact=L.ACT_ELU_OUT, want_f32=True)),
+        ("1x1 dgrad: elu' from out, bf16", gf11, lambda: ops.linear_dgrad(dy1, w11, aux=xa, dact=L.ACT_ELU_OUT)),
+        ("1x1 dgrad: plain bf16", gf11, lambda: ops.linear_dgrad(dy1, w11)),
+    ]
+    for name, gf, fn in rows:
+        ms = timeit(fn)
+        print(f"c4 variant  {name:40s} {ms * 1e3:8.1f} us  {gf / ms:8.1f} TFLOP/s", flush=True)
+
+
 which = sys.argv[1:] or ["c3", "c4"]
+if "v4" in which:
+    variants_c4()
 if "c4" in which:
     case("c4 2x2 256->256 (n=128, 32x32)", 128, 32, 32, 256, 256, 2, 2, (1, 1))
     case("c4 2x2 256->512", 128, 32, 32, 256, 512, 2, 2, (1, 1))
