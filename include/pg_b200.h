@@ -198,8 +198,9 @@ int pg_cast_f32_to_bf16(const float* x, void* y, int64_t numel, void* stream);
 int pg_causal_attn_fwd(const void* q, int64_t ld_q, const void* k, int64_t ld_k, const void* v, int64_t ld_v,
                        void* o, int64_t ld_o, float* lse, int N, int S, int H, int dk, int dv, float scale,
                        int strict, int impl, void* stream);
-/* Scratch: delta [N, H, S] fp32; dq_accum [N*S, H*dk] fp32, zero-filled by the caller (impl 0 only: dQ is
- * accumulated across key tiles with fp32 atomics, then rounded to bf16).  dq/dk/dv are bf16 pixel-major. */
+/* Scratch: delta [N, H, S] fp32; dq_accum [N*S, H*dk] fp32, contiguous, contents ignored on entry (the tcgen05
+ * kernels accumulate dQ across key tiles with fp32 bulk reduce-adds, then round it to bf16; the library clears the buffer
+ * itself, inside the delta pass; NULL for impl 1).  dq/dk/dv are bf16 pixel-major. */
 int pg_causal_attn_bwd(const void* q, int64_t ld_q, const void* k, int64_t ld_k, const void* v, int64_t ld_v,
                        const void* o, int64_t ld_o, const void* d_o, int64_t ld_do, const float* lse,
                        float* delta, float* dq_accum, void* dq, int64_t ld_dq, void* dk_, int64_t ld_dk,

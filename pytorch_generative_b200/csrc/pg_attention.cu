@@ -110,6 +110,14 @@ __global__ void attn_delta_kernel(const AttnArgs a) {
       a.delta[((size_t)n * a.H + h) * a.S + i] = s;
     }
   }
+  // The fp32 dQ accumulator of the tcgen05 backward is cleared here rather than by a separate memset: a pure write
+  // stream runs at ~3.7 TB/s on B200 (tools/micro/write_bw.py), this kernel is a pure read stream, together they overlap.
+  if (a.dq_accum != nullptr) {
+    float4* z = reinterpret_cast<float4*>(a.dq_accum);
+    const long long n4 = (long long)a.N * a.S * a.H * a.dk / 4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x)
+      z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
 }
 
 // Generic fallback (any dv): one warp per (row, head).
@@ -349,6 +357,8 @@ extern "C" int pg_causal_attn_bwd(const void* q, int64_t ld_q, const void* k, in
     attn_delta_kernel<<<(unsigned)blocks, 256, 0, stream>>>(a);
   } else {
     attn_delta_generic_kernel<<<(unsigned)((total * 32 + 255) / 256), 256, 0, stream>>>(a);
+    if (a.dq_accum != nullptr)
+      PG_CUDA(cudaMemsetAsync(a.dq_accum, 0, (size_t)N * S * H * dk * sizeof(float), stream));
   }
   if (pg_check_launch("pg_causal_attn_bwd(delta)")) return 1;
   if (impl == 1) {

@@ -227,6 +227,6 @@ def attn_fwd(q, k, v, n_img, seq, heads, dk_true, dv_slot, strict):
 def attn_bwd(q, k, v, o, do, lse, dq, dk, dv, n_img, seq, heads, dk_true, dv_slot, strict):
     P = q.shape[0]
     delta = empty((n_img, heads, seq), F32, q)
-    dq_acc = zeros((P, heads * HEAD_SLOT), F32, q) if ATTN_IMPL != 1 else None
+    dq_acc = empty((P, heads * HEAD_SLOT), F32, q) if ATTN_IMPL != 1 else None  # cleared by the library's delta pass
     L.causal_attn_bwd(q, k, v, o, do, lse, delta, dq_acc, dq, dk, dv, n_img, seq, heads, HEAD_SLOT, dv_slot, strict,
                       impl=ATTN_IMPL, dk_true=dk_true)

@@ -470,7 +470,7 @@ def test_attention_fwd_bwd(L, case, impl):
     dk_ = torch.full((P, H * ks), float("nan"), device=_dev(), dtype=torch.bfloat16)
     dv_ = torch.full((P, H * vs), float("nan"), device=_dev(), dtype=torch.bfloat16)
     delta = torch.empty(N, H, S, device=_dev())
-    dq_acc = torch.zeros(P, H * ks, device=_dev())
+    dq_acc = torch.full((P, H * ks), 7.0, device=_dev())  # scratch: the library clears it (contents ignored on entry)
     L.causal_attn_bwd(q, k, v, o, do, lse, delta, dq_acc, dq, dk_, dv_, N, S, H, ks, vs, strict, impl=impl, dk_true=dk)
     torch.cuda.synchronize()
     assert_close("attn dq", _from_slots(dq, H, dk, ks), dq_ref, rtol=2 ** -6, atol=2e-3)

@@ -30,7 +30,6 @@ def timeit(fn, reps=8):
 pairs = N * H * (S // 128) * (S // 128 + 1) // 2 * 128 * 128
 fwd = lambda: L.causal_attn_fwd(q, k, v, o, lse, N, S, H, D, D, False)
 def bwd(impl=0):
-    dq_acc.zero_()
     L.causal_attn_bwd(q, k, v, o, do, lse, delta, dq_acc, dqkv[:, :H * D], dqkv[:, H * D:2 * H * D], dqkv[:, 2 * H * D:], N, S, H, D, D,
                       False, impl=impl)
 t = timeit(fwd); print(f"attn fwd: {t*1e3:8.1f} us  {4*D*pairs/t/1e9:7.1f} TFLOP/s (tile-granular causal flops)")
