@@ -312,9 +312,9 @@ def run_ours(args):
     if sample_ms is not None:
         out["sample"] = {"n_samples": 16, "pixels": spec["shape"][1] * spec["shape"][2],
                          "ms_first_call": round(sample_ms[0], 1), "ms": round(sample_ms[1], 1),
-                         "method": "model.sample(n_samples=16): raster order and sample_fn hook of base.py:97-120; ImageGPT "
-                                   "evaluates each pixel incrementally (KV cache, graph-replayed step), the conv models "
-                                   "run one forward per pixel"}
+                         "method": "model.sample(n_samples=16): raster order and sample_fn hook of base.py:97-120; every "
+                                   "model evaluates each pixel incrementally (line buffers / KV caches, one graph-replayed "
+                                   "per-pixel program)"}
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(spec, steps=2, warmup=1)
     print(json.dumps(out), flush=True)
