@@ -44,6 +44,17 @@ class GenerativeModel(abc.ABC, nn.Module):
     def device(self):
         return next(self.parameters()).device
 
+    # Per-instance runtime caches (captured CUDA graphs of the samplers, line buffers, bf16 weight arenas keyed on the
+    # parameters' version counters, the data-parallel bucket hook) are rebuilt on demand and must not travel with a
+    # pickled or deep-copied model: a CUDA graph cannot be copied, and a copy must not replay the original's buffers.
+    _RUNTIME_CACHES = ("_sample_graphs", "_samplers", "_pixel_states", "_wcache", "_grad_bucket_hook")
+
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        for key in self._RUNTIME_CACHES:
+            state.pop(key, None)
+        return state
+
     @abc.abstractmethod
     def sample(self, n_samples):
         ...
