@@ -84,6 +84,8 @@ typedef struct pg_gemm_epilogue {
   int32_t dact;        /* activation whose derivative (at aux) scales the accumulator */
   int32_t accumulate;  /* 1: out_f32 is accumulated with fp32 atomics (split-K / grad accumulation) */
   float alpha;
+  float* bias_grad;    /* weight-gradient GEMMs only (a_mn_major = 1, impl 0), or NULL: fp32 [M] += sum_k A(m,k), i.e. the
+                        * bias gradient sum_p dY[p, cout] of the same layer, reduced from the staged A tiles */
 } pg_gemm_epilogue;
 
 /* impl: 0 = tcgen05/TMA kernel (the product); 1 = plain SIMT kernel kept as an on-device cross-check

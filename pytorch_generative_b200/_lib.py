@@ -37,6 +37,7 @@ class GemmEpilogue(ctypes.Structure):
         ("out_bf16", _vp), ("out_pre", _vp), ("out_f32", _vp),
         ("ld_aux", _i64), ("ld_res", _i64), ("ld_out_bf16", _i64), ("ld_out_pre", _i64), ("ld_out_f32", _i64),
         ("act", ctypes.c_int32), ("dact", ctypes.c_int32), ("accumulate", ctypes.c_int32), ("alpha", _f32),
+        ("bias_grad", _vp),
     ]
 
 
@@ -198,13 +199,15 @@ def reserve_sms(n):
 # ------------------------------------------------------------------------------------------------
 @_device_guarded
 def gemm(A, B, M, N, K, *, a_mn=False, b_mn=False, bias=None, aux=None, dact=ACT_NONE, res0=None, res1=None,
-         out_bf16=None, out_pre=None, out_f32=None, act=ACT_NONE, accumulate=False, alpha=1.0, split_k=1, impl=0):
-    """acc = A·Bᵀ (see pg_gemm_bf16 in include/pg_b200.h); all tensors are 2-D bf16/fp32 CUDA views."""
+         out_bf16=None, out_pre=None, out_f32=None, act=ACT_NONE, accumulate=False, alpha=1.0, split_k=1, impl=0,
+         bias_grad=None):
+    """acc = A·Bᵀ (see pg_gemm_bf16 in include/pg_b200.h); all tensors are 2-D bf16/fp32 CUDA views.
+    bias_grad (weight-gradient GEMMs, a_mn=True): fp32 [M] += sum_k A(m, k), reduced from the staged A tiles."""
     lib = load()
     assert A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16
     a_ptr, lda = _pm(A)
     b_ptr, ldb = _pm(B)
-    e = _epilogue(M, N, bias, aux, dact, res0, res1, out_bf16, out_pre, out_f32, act, accumulate, alpha)
+    e = _epilogue(M, N, bias, aux, dact, res0, res1, out_bf16, out_pre, out_f32, act, accumulate, alpha, bias_grad)
     hook = gemm_timing_hook
     if hook is not None:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -224,14 +227,15 @@ def _gemm_io(M, N, K, out_bf16, out_pre, out_f32, aux, res0, res1):
 
 @_device_guarded
 def gemm_conv(A, B, M, N, K, mode, n_img, H, W, C, taps, *, bias=None, aux=None, dact=ACT_NONE, res0=None, res1=None,
-              out_bf16=None, out_pre=None, out_f32=None, act=ACT_NONE, accumulate=False, alpha=1.0, split_k=1):
+              out_bf16=None, out_pre=None, out_f32=None, act=ACT_NONE, accumulate=False, alpha=1.0, split_k=1,
+              bias_grad=None):
     """Tap-loop convolution on the GEMM kernel (pg_gemm_bf16_conv); `taps` = [(dy, dx), ...] as the kernel applies them
     (the caller negates them for dgrad)."""
     lib = load()
     assert A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16
     a_ptr, lda = _pm(A)
     b_ptr, ldb = _pm(B)
-    e = _epilogue(M, N, bias, aux, dact, res0, res1, out_bf16, out_pre, out_f32, act, accumulate, alpha)
+    e = _epilogue(M, N, bias, aux, dact, res0, res1, out_bf16, out_pre, out_f32, act, accumulate, alpha, bias_grad)
     g = ConvGeom()
     g.mode, g.N, g.H, g.W, g.C, g.n_taps = mode, n_img, H, W, C, len(taps)
     for t, (dy, dx) in enumerate(taps):
@@ -258,8 +262,11 @@ def conv_gemm_supported(H, W, C):
     return C % 64 == 0 and 1 <= W <= 64 and 64 % W == 0 and (H * W) % 128 == 0
 
 
-def _epilogue(M, N, bias, aux, dact, res0, res1, out_bf16, out_pre, out_f32, act, accumulate, alpha):
+def _epilogue(M, N, bias, aux, dact, res0, res1, out_bf16, out_pre, out_f32, act, accumulate, alpha, bias_grad=None):
     e = GemmEpilogue()
+    if bias_grad is not None:
+        assert bias_grad.dtype == torch.float32 and bias_grad.numel() >= M and bias_grad.is_contiguous()
+    e.bias_grad = _ptr(bias_grad)
     e.bias = _ptr(bias)
     if bias is not None:
         assert bias.dtype == torch.float32 and bias.numel() >= N and bias.is_contiguous()

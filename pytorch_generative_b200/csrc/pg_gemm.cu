@@ -58,6 +58,7 @@ struct GemmParams {
   int staged;
   int store_deriv;  // out_pre receives act'(pre) (PG_ACT_STORE_DERIV)
   int res_bf16;     // res0 / res1 are bf16 matrices (PG_ACT_RES_BF16)
+  float* a_rowsum;  // MN-major A only: fp32 [M] += sum_k A(m, k) (pg_gemm_epilogue.bias_grad), nullptr = off
   int epi_depth;    // staging stages per epilogue warpgroup (1 or 2)
   int epi_stage_bytes;
   int off_res0, off_res1, off_aux, off_outf, off_outb, off_outp;  // slab offsets inside an epilogue stage, -1 = absent
@@ -278,7 +279,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
+      // freed by the MMAs' commit and, when the side reduction over A is on, by its two warps as well
+      mbar_init(&empty_bar[i], (A_MN && p.a_rowsum != nullptr) ? 3 : 1);
     }
     for (int i = 0; i < ACC_STAGES; ++i) {
       mbar_init(&tfull_bar[i], 1);
@@ -426,6 +428,62 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (TWO) umma_commit_2sm_w(&tfull_bar[as]);
         else umma_commit_w(&tfull_bar[as]);
         if (++as == ACC_STAGES) { as = 0; aph ^= 1; }
+      }
+    }
+  } else if (A_MN && warp < 4) {
+    // ===================== warps 2-3, weight-gradient GEMMs: bias gradient from the staged A tiles =====================
+    // A = dY read MN-major, so sum_k A(m, k) is the bias gradient of the layer whose weight gradient this launch
+    // computes.  The two otherwise idle warps add up every A stage while the MMAs run (16 KB of shared-memory reads per
+    // 48 KB operand stage) — the separate column-sum pass re-read dY from HBM.  Only the CTAs of N block 0 do it (every
+    // (m block, split) is seen once); partial sums go to a_rowsum with fp32 atomics, like the split-K tiles.
+    if (p.a_rowsum != nullptr) {
+      const int t = (warp - 2) * 32 + lane;   // 0..63
+      const int c = t & 15, g = t >> 4;        // 16-byte chunk (8 consecutive m) of the 128-wide tile, k-row group
+      const uint32_t atom = (uint32_t)(c >> 3) * (BK * 128), cc = (uint32_t)(c & 7);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = tile_first; tile < num_tiles; tile += tile_stride) {
+        const int n_blk = tile % p.num_n_blk;
+        const int rest = tile / p.num_n_blk;
+        const int m_blk = rest % p.num_m_blk;
+        const int ks = rest / p.num_m_blk;
+        const int k0 = ks * p.k_per_split;
+        const int k1 = min(k0 + p.k_per_split, p.k_iters);
+        const bool mine = (n_blk == 0);
+        float acc[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+        for (int kit = k0; kit < k1; ++kit) {
+          mbar_wait(&full_bar[s], ph);
+          if (mine) {
+            const uint8_t* sA = smem + s * STAGE_BYTES + atom;
+#pragma unroll
+            for (int i = 0; i < BK / 4; ++i) {
+              const uint32_t k = (uint32_t)(g + 4 * i);
+              const uint4 w = *reinterpret_cast<const uint4*>(sA + k * 128 + ((cc ^ (k & 7u)) << 4));
+              const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 f = unpack_bf16x2(ww[j]);
+                acc[2 * j] += f.x;
+                acc[2 * j + 1] += f.y;
+              }
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty_bar[s]);   // release: this warp's reads of the stage are done
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+        if (mine) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], 16);  // the warp's two k-row groups
+          if (lane < 16) {
+            const int m0 = m_blk * BM + c * 8;
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              if (m0 + q < p.M) atomicAdd(p.a_rowsum + m0 + q, acc[q]);
+          }
+        }
       }
     }
   } else if (warp >= 4) {
@@ -891,6 +949,9 @@ static int gemm_entry(const void* A, int a_mn_major, int64_t lda, const void* B,
   p.store_deriv = (epi->act & PG_ACT_STORE_DERIV) ? 1 : 0;
   p.res_bf16 = (epi->act & PG_ACT_RES_BF16) ? 1 : 0;
   p.epi.act = epi->act & 0xff;
+  p.a_rowsum = epi->bias_grad;
+  PG_REQUIRE(!epi->bias_grad || (a_mn_major && impl == 0),
+             "pg_gemm_bf16: bias_grad rides on the weight-gradient GEMM (a_mn_major = 1, impl 0)");
   PG_REQUIRE(!p.store_deriv || epi->out_pre, "pg_gemm_bf16: PG_ACT_STORE_DERIV needs out_pre");
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   p.vec_ok = 1;

@@ -178,9 +178,10 @@ class _ImageGPTStack(torch.autograd.Function):
             ops.linear_wgrad(dx_b, blk["g"], dw2)
             grads[base_i + 12] = dw2.view(C, 4 * C, 1, 1)
             du = ops.linear_dgrad(dx_b, blk["w2"], aux=blk["u"], dact=L.ACT_GIVEN)
-            grads[base_i + 11] = ops.bias_grad(du, out=carve_small(b, 6 * C + qkv_rows, 4 * C))
+            # the bias gradient (column sums of du) is reduced by the wgrad launch from the du tiles it stages
+            grads[base_i + 11] = carve_small(b, 6 * C + qkv_rows, 4 * C)
             dw1 = carve(b, 4 * C * C, 4 * C, C)
-            ops.linear_wgrad(du, blk["a2"], dw1)
+            ops.linear_wgrad(du, blk["a2"], dw1, db_out=grads[base_i + 11])
             grads[base_i + 10] = dw1.view(4 * C, C, 1, 1)
             da2 = ops.linear_dgrad(du, blk["w1"])
             del du
@@ -200,9 +201,9 @@ class _ImageGPTStack(torch.autograd.Function):
             ops.attn_bwd(q, k, v, blk["o"], do, blk["lse"], dqkv[:, : H * slot], dqkv[:, H * slot: 2 * H * slot],
                          dqkv[:, 2 * H * slot:], n, S, H, meta["dk"], dv_slot, False)
             del do
-            dbqkv = ops.bias_grad(dqkv, out=carve_small(b, 6 * C, qkv_rows))
+            dbqkv = carve_small(b, 6 * C, qkv_rows)
             dwqkv = carve(b, 8 * C * C + C * H * dv_slot, qkv_rows, C)
-            ops.linear_wgrad(dqkv, blk["a1"], dwqkv)
+            ops.linear_wgrad(dqkv, blk["a1"], dwqkv, db_out=dbqkv)
             if meta["identity"]:  # heads fill their slots: plain slices of the fused gradient buffers
                 grads[base_i + 2] = dwqkv[:C].view(C, C, 1, 1)
                 grads[base_i + 3] = dbqkv[:C]

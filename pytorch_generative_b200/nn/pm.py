@@ -252,15 +252,19 @@ class _Conv(torch.autograd.Function):
         else:  # a handful of output channels (the logits): pad the operand to the 16-byte TMA pitch
             dyb = torch.zeros(dy.shape[0], cout_p, dtype=BF16, device=dy.device)
             dyb[:, :cout] = dy
-        db = ops.bias_grad(dyb[:, :cout]) if has_bias else None
-        dw = None
+        db = dw = None
         if ctx.needs_input_grad[2]:
+            # weight and bias gradient in one launch: the wgrad GEMM reduces the dy tiles it stages (ops.linear_wgrad)
             dwcat = torch.zeros(cout_p, T * cin_p, dtype=F32, device=dy.device)
+            dbp = torch.zeros(cout_p, dtype=F32, device=dy.device) if has_bias else None
             if pointwise:
-                ops.linear_wgrad(dyb, xa, dwcat)
+                ops.linear_wgrad(dyb, xa, dwcat, db_out=dbp)
             else:
-                ops.conv_wgrad(dyb, xa, dwcat, geom.n, geom.h, geom.w, taps)
+                ops.conv_wgrad(dyb, xa, dwcat, geom.n, geom.h, geom.w, taps, db_out=dbp)
             dw = dwcat[:cout].view(cout, kh, kw, cin_p)[..., :cin].permute(0, 3, 1, 2).contiguous()
+            db = dbp[:cout] if has_bias else None
+        elif has_bias:
+            db = ops.bias_grad(dyb[:, :cout])
         dx = None
         if ctx.needs_input_grad[0]:
             want_f32 = x_dtype == F32

@@ -123,13 +123,18 @@ def _split_k_for(m_out, n_out, k):
     return max(1, min(want, k_iters // 8 if k_iters >= 16 else 1))
 
 
-def linear_wgrad(dy, a, dw_out):
-    """dw_out[Cout, Cin] += dy.T @ a over the pixel dimension (fp32 atomics, split along pixels)."""
+def linear_wgrad(dy, a, dw_out, db_out=None):
+    """dw_out[Cout, Cin] += dy.T @ a over the pixel dimension (fp32 atomics, split along pixels).
+    db_out (fp32 [Cout], pre-zeroed or holding a running sum): += column sums of dy, reduced by the same launch from the
+    dy tiles it stages anyway (the bias gradient without a second pass over dy)."""
     P, cout = dy.shape
     cin = a.shape[1]
     assert dw_out.dtype == F32 and dw_out.shape[0] >= cout
+    if db_out is not None and GEMM_IMPL != 0:   # the SIMT cross-check build of the stacks: separate column sums
+        L.colsum(dy, db_out, accumulate=True)
+        db_out = None
     L.gemm(dy, a, cout, cin, P, a_mn=True, b_mn=True, out_f32=dw_out, accumulate=True,
-           split_k=_split_k_for(cout, cin, P), impl=GEMM_IMPL)
+           split_k=_split_k_for(cout, cin, P), impl=GEMM_IMPL, bias_grad=db_out)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -160,8 +165,9 @@ def conv_dgrad(dy, wcat, cin, n_img, h, w, taps, *, aux=None, dact=L.ACT_NONE, w
     return ob, of
 
 
-def conv_wgrad(dy, x, dw_out, n_img, h, w, taps):
-    """dw_out[Cout, T*C] += sum_p dy[p]^T . x[p + taps[t]] (fp32 accumulation, split along pixels)."""
+def conv_wgrad(dy, x, dw_out, n_img, h, w, taps, db_out=None):
+    """dw_out[Cout, T*C] += sum_p dy[p]^T . x[p + taps[t]] (fp32 accumulation, split along pixels); db_out as in
+    linear_wgrad."""
     P, cout = dy.shape
     C = x.shape[1]
     T = len(taps)
@@ -170,7 +176,8 @@ def conv_wgrad(dy, x, dw_out, n_img, h, w, taps):
     tiles = ((cout + 127) // 128) * (T * C // bn)
     k_iters = (P + 63) // 64
     split = max(1, min(max(1, L.sm_count() // tiles), k_iters // 8 if k_iters >= 16 else 1))
-    L.gemm_conv(dy, x, cout, T * C, P, L.CONV_WGRAD, n_img, h, w, C, taps, out_f32=dw_out, accumulate=True, split_k=split)
+    L.gemm_conv(dy, x, cout, T * C, P, L.CONV_WGRAD, n_img, h, w, C, taps, out_f32=dw_out, accumulate=True, split_k=split,
+                bias_grad=db_out)
 
 
 def bias_grad(dy, out=None):

@@ -217,6 +217,22 @@ def test_gemm_wgrad_splitk_accumulate(L, split_k):
     assert_close(f"wgrad split_k={split_k}", out, ref + 1.0, rtol=2e-5, atol=1e-3)
 
 
+@pytest.mark.parametrize("Cout,Cin,P,split_k", [(256, 192, 4096, 1), (256, 192, 4096, 3), (1536, 512, 8192, 6),
+                                                (24, 64, 1000, 1), (520, 128, 12352, 8), (2048, 512, 65536, 4)])
+def test_gemm_wgrad_with_bias_gradient(L, Cout, Cin, P, split_k):
+    """pg_gemm_epilogue.bias_grad: the weight-gradient launch also reduces the dY tiles it stages into the bias gradient
+    (partial M / K tiles, split-K, several tiles per CTA); dW must be unchanged by it."""
+    A, B, ref = _operands(Cout, Cin, P, True, True, seed=41)     # A = dY read MN-major: A[k, m] = dY[pixel k, cout m]
+    dw = torch.zeros(Cout, Cin, device=_dev())
+    db = torch.full((Cout,), -1.0, device=_dev())
+    L.gemm(A, B, Cout, Cin, P, a_mn=True, b_mn=True, out_f32=dw, accumulate=True, split_k=split_k, bias_grad=db)
+    torch.cuda.synchronize()
+    assert_close("dW", dw, ref, rtol=2e-5, atol=1e-3 * (P / 4096) ** 0.5)
+    assert_close("db", db, A.float().sum(0) - 1.0, rtol=1e-4, atol=1e-3 * (P / 4096) ** 0.5)
+    with pytest.raises(RuntimeError, match="bias_grad"):  # not a weight-gradient GEMM
+        L.gemm(B, B, 64, 64, 64, out_f32=torch.zeros(64, 64, device=_dev()), bias_grad=torch.zeros(64, device=_dev()))
+
+
 @pytest.mark.parametrize("M,N,K", [(16, 2048, 512), (2, 96, 32), (32, 520, 2048), (5, 3, 64)])
 def test_gemm_skinny_rows(L, M, N, K):
     """M <= 32 rows (the per-pixel step of incremental sampling) takes the skinny kernel: same epilogue semantics."""
@@ -525,8 +541,10 @@ def test_conv_gemm_fwd_dgrad_wgrad(L, case):
     _, _, y = ops.conv_fwd(x, wcat, bias, N, H, W, taps, want_bf16=False, want_f32=True)
     dxb, dxf = ops.conv_dgrad(dy, wcat, Cin, N, H, W, taps, want_f32=True)
     dw = torch.zeros(Cout, T * Cin, device=_dev())
-    ops.conv_wgrad(dy, x, dw, N, H, W, taps)
+    db = torch.full((Cout,), 2.0, device=_dev())  # the bias gradient rides on the wgrad launch and accumulates
+    ops.conv_wgrad(dy, x, dw, N, H, W, taps, db_out=db)
     torch.cuda.synchronize()
+    assert_close("conv gemm db", db, dy.float().sum(0) + 2.0, rtol=1e-4, atol=1e-3 * (P ** 0.5))
     assert_close("conv gemm y", y, y_ref.detach(), rtol=1e-3, atol=1e-3)
     assert_close("conv gemm dx", dxf, xr.grad.reshape(P, Cin), rtol=1e-3, atol=1e-3)
     assert_close("conv gemm dx bf16", dxb, xr.grad.reshape(P, Cin), rtol=2 ** -7, atol=1e-2)
