@@ -34,7 +34,8 @@ rows.append(("attention bwd (+ delta, dQ zero / convert)", 10.0 * D * tiles, 5 *
 rows.append(("LayerNorm fwd (x2)", 0, X * f32, X * bf, 38.9))
 rows.append(("LayerNorm-2 bwd (1 residual grad)", 0, X * (bf + f32 + f32), X * (f32 + bf), 104.5))
 rows.append(("LayerNorm-1 bwd (2 residual grads)", 0, X * (bf + f32 + f32 + f32), X * (f32 + bf), 118.8))
-rows.append(("bias-grad column sums (dqkv, dh)", 0, 3 * X * bf + 4 * X * bf, 0, 2 * 38.6))
+# the bias gradients of the qkv and fc1 layers ride on their wgrad launches since the end of round 2 (before: two
+# column-sum passes, 470 MB read, 77 us per block)
 
 print("| kernel | GFLOP | read MB | written MB | ideal us (bound) | measured us | fraction |")
 print("|---|---|---|---|---|---|---|")
@@ -48,4 +49,4 @@ for name, fl, rd, wr, us in rows:
     tm += us * mult
     print(f"| {name} | {fl / 1e9:.1f} | {rd / 1e6:.0f} | {wr / 1e6:.0f} | {ideal:.1f} ({bound}) | {us:.1f} | {ideal / us:.2f} |")
 print(f"| **block total** | | | | {ti:.0f} | {tm:.0f} | {ti / tm:.2f} |")
-print(f"\n24 blocks: ideal {24 * ti / 1e3:.1f} ms, measured kernels {24 * tm / 1e3:.1f} ms (step 60.6 ms incl. Adam, clip, input / output layers, host gaps)")
+print(f"\n24 blocks: ideal {24 * ti / 1e3:.1f} ms, measured kernels {24 * tm / 1e3:.1f} ms (step 60.5 ms incl. Adam, clip, input / output layers, host gaps)")
