@@ -5,7 +5,6 @@ the reference's `nn.Sequential`s are not separate ops here: each one is fused in
 (`pre_act`), so a block is three kernels-backed convs: 1x1, masked 3x3 (type B), 1x1.
 """
 
-import torch
 from torch import nn
 
 from .. import _lib as L
